@@ -1,0 +1,192 @@
+/*
+ * dreamzs.h -- C ABI of the B200-native MT-DREAM(ZS) step path (libdreamzs.so).
+ *
+ * The reference (LoLab-MSM/PyDREAM) is pure Python and has no FFI: the boundary this
+ * library sits behind is the Python operator interface
+ *     Dream.astep(q0, T, last_loglike, last_logprior) -> (q_new, log_prior, log_like)
+ *                                                          pydream/Dream.py:193-422
+ *     _sample_dream's per-chain loop over astep             pydream/core.py:89-129
+ *     Gelman_Rubin(sampled_parameters) -> Rhat[d]           pydream/convergence.py:3-20
+ * Every entry point below names the reference code it replaces.  INTEGRATION.md shows
+ * the ctypes stub a PyDREAM maintainer would add to bind them.
+ *
+ * Conventions
+ *   - all pointers marked "device" are CUDA device pointers owned by the caller; the
+ *     library never allocates, frees or keeps them; there is no global state.
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), does
+ *     not synchronise the host, and returns 0 on success or a negative DREAMZS_E_* code.
+ *   - all floating-point state is float64; chain ids are GLOBAL ids (shard-independent
+ *     random streams: results do not depend on how chains are split over GPUs).
+ *   - random numbers: Philox4x32-10, key=(seed lo, seed hi),
+ *     counter=(block, call_no<<3|stream, iteration, global chain id); see
+ *     DESIGN.md "RNG contract".
+ */
+#ifndef DREAMZS_H
+#define DREAMZS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DREAMZS_ABI_VERSION 1
+
+/* status codes */
+#define DREAMZS_OK 0
+#define DREAMZS_E_BADARG (-1)     /* inconsistent sizes / null pointers / unsupported option */
+#define DREAMZS_E_LAUNCH (-2)     /* cudaGetLastError() != cudaSuccess after the launch */
+#define DREAMZS_E_UNSUPPORTED (-3)/* option combination the kernels do not implement */
+
+/* limits baked into the kernels */
+#define DREAMZS_MAX_NCR 16
+#define DREAMZS_MAX_NGAMMA 8
+#define DREAMZS_MAX_DEPAIRS 8
+#define DREAMZS_MAX_MULTITRY 16
+#define DREAMZS_MAX_NDIM 1024
+
+/* analytic log-likelihoods evaluated in-register (pydream_b200/targets.py) */
+enum dreamzs_target_kind {
+  DREAMZS_TARGET_CONSTANT = 0,       /* table = [value]                                  */
+  DREAMZS_TARGET_GAUSSIAN_DENSE = 1, /* table = [log_F, invC (d*d row-major)]            */
+  DREAMZS_TARGET_MIXTURE = 2,        /* table = [log_F0, log_F1, mu0[d], mu1[d]]         */
+  DREAMZS_TARGET_BANANA = 3,         /* table = [b, var1]                                */
+  DREAMZS_TARGET_SUMSHIFT = 4,       /* table = [shift]                                  */
+  DREAMZS_TARGET_EXTERNAL = 5        /* log-likelihood supplied by the caller (split step) */
+};
+
+/* per-dimension prior kinds (pydream/parameters.py:19-70 restricted to closed forms) */
+enum dreamzs_prior_kind {
+  DREAMZS_PRIOR_FLAT = 0,    /* FlatParam: log prior 0, bounds +-inf            */
+  DREAMZS_PRIOR_NORMAL = 1,  /* scipy.stats.norm(loc=a, scale=b)                */
+  DREAMZS_PRIOR_UNIFORM = 2  /* scipy.stats.uniform(loc=a, scale=b): [a, a+b]   */
+};
+
+/* Options of the sampler: the subset of Dream.__init__ (pydream/Dream.py:63-191) that
+ * the step reads, plus the shard geometry. */
+typedef struct dreamzs_config {
+  int32_t abi_version;      /* DREAMZS_ABI_VERSION */
+  int32_t ndim;             /* total_var_dimension, Dream.py:81-83 */
+  int32_t ld;               /* row stride (doubles) of Z, X and the trace; multiple of 4, >= ndim */
+  int32_t nchains_global;   /* N over all shards */
+  int32_t chain_begin;      /* first global chain id of this shard */
+  int32_t nchains_local;    /* chains in this shard */
+  int32_t nCR;              /* Dream.py:108-112 */
+  int32_t ngamma;           /* gamma_levels, Dream.py:120 */
+  int32_t nDEpairs;         /* len(self.DEpairs), Dream.py:150 */
+  int32_t multitry;         /* 1 = off, Dream.py:155-161 */
+  int32_t hardboundaries;   /* Dream.py:80 */
+  int32_t history_thin;     /* Dream.py:188 */
+  int32_t target_kind;      /* enum dreamzs_target_kind */
+  int32_t reserved0;
+  double snooker;           /* Dream.py:152 */
+  double p_gamma_unity;     /* Dream.py:153 */
+  double lamb;              /* Dream.py:164 */
+  double zeta;              /* Dream.py:165 */
+  uint64_t seed;            /* Philox key */
+} dreamzs_config;
+
+/* Device-resident sampler state (all device pointers). */
+typedef struct dreamzs_state {
+  double *Z;                 /* archive, rows x ld (Dream_shared_vars.history, core.py:281) */
+  int64_t Z_capacity_rows;
+  double *X;                 /* current positions, nchains_local x ld */
+  double *last_prior;        /* nchains_local (Dream.last_prior)  */
+  double *last_like;         /* nchains_local (Dream.last_like)   */
+  const double *cr_probs;    /* nCR    (Dream_shared_vars.cross_probs)        */
+  const double *gamma_probs; /* ngamma (Dream_shared_vars.gamma_level_probs)  */
+  const double *gamma_table; /* ngamma x nDEpairs x ndim (Dream.gamma_arr, Dream.py:173-179) */
+  const double *target_table;/* see dreamzs_target_kind */
+  const int32_t *prior_kind; /* ndim */
+  const double *prior_a;     /* ndim */
+  const double *prior_b;     /* ndim */
+  const double *mins;        /* ndim (Dream.mins, Dream.py:86-105) */
+  const double *maxs;        /* ndim */
+} dreamzs_state;
+
+/* Per-launch outputs (device pointers; any may be NULL except trace/trace_logp). */
+typedef struct dreamzs_trace {
+  double *trace;        /* nchains_local x trace_iters x ld : sampled_params, core.py:99,114 */
+  double *trace_logp;   /* nchains_local x trace_iters     : log_ps = like + prior, core.py:115 */
+  uint32_t *decisions;  /* nchains_local x trace_iters : bit0 accept (state changed), bit1 snooker,
+                           bits2-5 CR index, bits6-9 gamma-level index, bits10-13 DE pairs,
+                           bits14-17 selected multi-try index, bit18 gamma==1 flag used by CR adaptation,
+                           bit19 metropolis accepted */
+  int64_t trace_iters;  /* iterations the trace buffers hold per chain */
+  int64_t trace_offset; /* trace row that iteration `iter_begin` writes to */
+} dreamzs_trace;
+
+int dreamzs_abi_version(void);
+
+/* Initial log-prior / log-likelihood of the current positions X (first-call branch of
+ * astep, Dream.py:266-268 -> Model.total_logp, pydream/model.py:17-32). */
+int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state *st, void *stream);
+
+/* `niter` fused iterations iter_begin .. iter_begin+niter-1 of Dream.astep for every
+ * local chain (Dream.py:193-362: set_snooker/set_CR/set_DEpair/set_gamma_level,
+ * generate_proposal_points, snooker_update, Model.total_logp on analytic targets,
+ * mt_evaluate_logps / mt_choose_proposal_pt, metrop_select, record_history).
+ * `archive_rows` = count + nseedchains visible to the FIRST iteration.  The archive must
+ * be constant over the launch except for the append made by the LAST iteration of the
+ * launch: the caller guarantees that at most the last iteration satisfies
+ * iter % history_thin == 0.  That iteration writes chain c's new state to row
+ * archive_rows + (global chain id) (record_history, Dream.py:919-938, in chain order). */
+int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
+                 int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream);
+
+/* Split step for caller-supplied log-likelihoods (target_kind EXTERNAL), the batched form of
+ * mt_evaluate_logps (Dream.py:839-881).  `propose` writes the points to evaluate for one
+ * phase (phase 0: multitry proposals around X; phase 1: multitry-1 reference points around
+ * the selected proposal); the caller fills ext_prior/ext_like; `finish` runs selection
+ * (phase 0, multitry>1) or the Metropolis accept + bookkeeping (last phase).
+ * points: nchains_local x multitry x ld.  scratch: dreamzs_split_scratch_bytes(). */
+int64_t dreamzs_split_scratch_bytes(const dreamzs_config *cfg);
+int dreamzs_split_propose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter,
+                          int32_t phase, int64_t archive_rows, double *points, void *scratch,
+                          void *stream);
+int dreamzs_split_finish(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
+                         int64_t iter, int32_t phase, int64_t archive_rows, const double *points,
+                         const double *ext_prior, const double *ext_like, void *scratch,
+                         void *stream);
+
+/* Crossover-probability (and gamma-level) adaptation for ONE iteration of the burn-in
+ * (estimate_crossover_probabilities, Dream.py:451-499; estimate_gamma_level_probs,
+ * Dream.py:501-540; set_current_position_arr, Dream.py:424-449).
+ *   stage 0: colsum[d]  += sum_c X_new[c]            (local shard; caller all-reduces)
+ *   stage 1: colsq[d]   += sum_c (X_new[c]-mean)^2   (mean = colsum / N; caller all-reduces)
+ *   stage 2: partial[2*nCR (+2*ngamma)] = per-index update counts and summed squared
+ *            normalised jumps of the local chains (caller all-reduces and folds them into
+ *            ncr_updates / delta_m and renormalises the probabilities on the host side
+ *            of the ABI -- see dreamzs_adapt_finish).
+ * x_old: states before the iteration (nchains_local x ld_old), decisions: this iteration's
+ * decision words (stride dec_stride).  final_update != 0 reproduces the unconditional update
+ * made at iter == crossover_burnin (Dream.py:391-401). */
+int dreamzs_adapt_colsum(const dreamzs_config *cfg, const double *X_new, double *colsum, void *stream);
+int dreamzs_adapt_colsq(const dreamzs_config *cfg, const double *X_new, const double *colsum,
+                        double *colsq, void *stream);
+int dreamzs_adapt_jumps(const dreamzs_config *cfg, const double *X_new, const double *x_old,
+                        int64_t ld_old, const uint32_t *decisions, int64_t dec_stride,
+                        const double *colsq, int32_t final_update, int32_t adapt_gamma,
+                        double *partial, void *stream);
+/* Fold all-reduced partials into the shared adaptation state and renormalise
+ * (Dream.py:483-495, 527-538).  All pointers device; runs as one tiny kernel. */
+int dreamzs_adapt_finish(const dreamzs_config *cfg, const double *partial, int32_t adapt_crossover,
+                         int32_t adapt_gamma, double *ncr_updates, double *delta_m, double *cr_probs,
+                         double *ngamma_updates, double *delta_m_gamma, double *gamma_probs,
+                         void *stream);
+
+/* Gelman-Rubin diagnostic (pydream/convergence.py:3-20) in three stream-ordered stages so
+ * that chains may be sharded:
+ *   chain_stats: per local chain, mean[d] and var[d] (ddof 0) of trace rows nburnin..nsamples-1
+ *   caller all-gathers / concatenates the per-chain stats over shards
+ *   finish: W = mean_c var, B = var_c(mean) (ddof 0), Rhat = sqrt((W (1-1/nsamples) + B)/W) */
+int dreamzs_gr_chain_stats(const double *trace, int64_t nchains, int64_t nsamples, int64_t nburnin,
+                           int32_t ndim, int64_t ld, double *chain_mean, double *chain_var,
+                           void *stream);
+int dreamzs_gr_finish(const double *chain_mean, const double *chain_var, int64_t nchains,
+                      int64_t nsamples, int32_t ndim, double *rhat, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DREAMZS_H */
