@@ -45,10 +45,13 @@ extern "C" {
 #define DREAMZS_MAX_MULTITRY 16
 #define DREAMZS_MAX_NDIM 1024
 
+/* dreamzs_config.flags */
+#define DREAMZS_FLAG_ALL_FLAT 1  /* every prior is FLAT: the kernels skip prior evaluation and bounds */
+
 /* analytic log-likelihoods evaluated in-register (pydream_b200/targets.py) */
 enum dreamzs_target_kind {
   DREAMZS_TARGET_CONSTANT = 0,       /* table = [value]                                  */
-  DREAMZS_TARGET_GAUSSIAN_DENSE = 1, /* table = [log_F, invC (d*d row-major)]            */
+  DREAMZS_TARGET_GAUSSIAN_DENSE = 1, /* table = [log_F, 0, invC^T (d rows, row stride ld)] */
   DREAMZS_TARGET_MIXTURE = 2,        /* table = [log_F0, log_F1, mu0[d], mu1[d]]         */
   DREAMZS_TARGET_BANANA = 3,         /* table = [b, var1]                                */
   DREAMZS_TARGET_SUMSHIFT = 4,       /* table = [shift]                                  */
@@ -78,7 +81,7 @@ typedef struct dreamzs_config {
   int32_t hardboundaries;   /* Dream.py:80 */
   int32_t history_thin;     /* Dream.py:188 */
   int32_t target_kind;      /* enum dreamzs_target_kind */
-  int32_t reserved0;
+  int32_t flags;            /* DREAMZS_FLAG_* */
   double snooker;           /* Dream.py:152 */
   double p_gamma_unity;     /* Dream.py:153 */
   double lamb;              /* Dream.py:164 */
@@ -134,46 +137,33 @@ int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state *st, void *
 int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                  int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream);
 
-/* Split step for caller-supplied log-likelihoods (target_kind EXTERNAL), the batched form of
- * mt_evaluate_logps (Dream.py:839-881).  `propose` writes the points to evaluate for one
- * phase (phase 0: multitry proposals around X; phase 1: multitry-1 reference points around
- * the selected proposal); the caller fills ext_prior/ext_like; `finish` runs selection
- * (phase 0, multitry>1) or the Metropolis accept + bookkeeping (last phase).
- * points: nchains_local x multitry x ld.  scratch: dreamzs_split_scratch_bytes(). */
-int64_t dreamzs_split_scratch_bytes(const dreamzs_config *cfg);
-int dreamzs_split_propose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter,
-                          int32_t phase, int64_t archive_rows, double *points, void *scratch,
-                          void *stream);
-int dreamzs_split_finish(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
-                         int64_t iter, int32_t phase, int64_t archive_rows, const double *points,
-                         const double *ext_prior, const double *ext_like, void *scratch,
-                         void *stream);
-
 /* Crossover-probability (and gamma-level) adaptation for ONE iteration of the burn-in
  * (estimate_crossover_probabilities, Dream.py:451-499; estimate_gamma_level_probs,
- * Dream.py:501-540; set_current_position_arr, Dream.py:424-449).
- *   stage 0: colsum[d]  += sum_c X_new[c]            (local shard; caller all-reduces)
- *   stage 1: colsq[d]   += sum_c (X_new[c]-mean)^2   (mean = colsum / N; caller all-reduces)
- *   stage 2: partial[2*nCR (+2*ngamma)] = per-index update counts and summed squared
- *            normalised jumps of the local chains (caller all-reduces and folds them into
- *            ncr_updates / delta_m and renormalises the probabilities on the host side
- *            of the ABI -- see dreamzs_adapt_finish).
- * x_old: states before the iteration (nchains_local x ld_old), decisions: this iteration's
- * decision words (stride dec_stride).  final_update != 0 reproduces the unconditional update
- * made at iter == crossover_burnin (Dream.py:391-401). */
-int dreamzs_adapt_colsum(const dreamzs_config *cfg, const double *X_new, double *colsum, void *stream);
-int dreamzs_adapt_colsq(const dreamzs_config *cfg, const double *X_new, const double *colsum,
-                        double *colsq, void *stream);
-int dreamzs_adapt_jumps(const dreamzs_config *cfg, const double *X_new, const double *x_old,
-                        int64_t ld_old, const uint32_t *decisions, int64_t dec_stride,
-                        const double *colsq, int32_t final_update, int32_t adapt_gamma,
-                        double *partial, void *stream);
-/* Fold all-reduced partials into the shared adaptation state and renormalise
- * (Dream.py:483-495, 527-538).  All pointers device; runs as one tiny kernel. */
+ * Dream.py:501-540; set_current_position_arr, Dream.py:424-449), as stream-ordered reduction
+ * stages so that chains may be sharded (the caller all-reduces between stages when sharded):
+ *   colsum : colsum[d]  = sum over LOCAL chains of X_new[c]
+ *   colsq  : colsq[d]   = sum over LOCAL chains of (X_new[c] - colsum_global/N)^2   (np.std is two-pass)
+ *   jumps  : partial[2*nCR + 2*ngamma] = for the LOCAL chains, per CR index the number of updates and
+ *            the summed squared normalised jump (then the same per gamma level); sd = sqrt(colsq_global/N).
+ *            Which chains count follows Dream.py:371-383 from this iteration's decision words
+ *            (stride dec_stride); final_update != 0 is the unconditional update at
+ *            iter == crossover_burnin (Dream.py:391-401).  x_old: states before the iteration,
+ *            chain stride ld_old doubles.
+ *   finish : folds the (all-reduced) partials into ncr_updates/delta_m (and the gamma twins) and
+ *            renormalises the probabilities once every delta_m is non-zero (Dream.py:483-495).
+ * workspace: dreamzs_adapt_workspace_bytes(cfg) bytes of device memory. */
+int64_t dreamzs_adapt_workspace_bytes(const dreamzs_config *cfg);
+int dreamzs_adapt_colsum(const dreamzs_config *cfg, const double *X_new, double *colsum, void *workspace,
+                         void *stream);
+int dreamzs_adapt_colsq(const dreamzs_config *cfg, const double *X_new, const double *colsum, double *colsq,
+                        void *workspace, void *stream);
+int dreamzs_adapt_jumps(const dreamzs_config *cfg, const double *X_new, const double *x_old, int64_t ld_old,
+                        const uint32_t *decisions, int64_t dec_stride, const double *colsq,
+                        int32_t final_update, int32_t adapt_crossover, int32_t adapt_gamma, double *partial,
+                        void *workspace, void *stream);
 int dreamzs_adapt_finish(const dreamzs_config *cfg, const double *partial, int32_t adapt_crossover,
                          int32_t adapt_gamma, double *ncr_updates, double *delta_m, double *cr_probs,
-                         double *ngamma_updates, double *delta_m_gamma, double *gamma_probs,
-                         void *stream);
+                         double *ngamma_updates, double *delta_m_gamma, double *gamma_probs, void *stream);
 
 /* Gelman-Rubin diagnostic (pydream/convergence.py:3-20) in three stream-ordered stages so
  * that chains may be sharded:

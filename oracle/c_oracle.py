@@ -14,7 +14,7 @@ MAX_NCR, MAX_NGAMMA = 16, 8
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'abi_version', 'ndim', 'ld', 'nchains_global', 'chain_begin', 'nchains_local', 'nCR', 'ngamma', 'nDEpairs',
-        'multitry', 'hardboundaries', 'history_thin', 'target_kind', 'reserved0')] + [
+        'multitry', 'hardboundaries', 'history_thin', 'target_kind', 'flags')] + [
         ('snooker', C.c_double), ('p_gamma_unity', C.c_double), ('lamb', C.c_double), ('zeta', C.c_double),
         ('seed', C.c_uint64)]
 

@@ -1,0 +1,88 @@
+"""ctypes binding of libdreamzs.so (include/dreamzs.h).  No torch types cross this boundary:
+device pointers are passed as integers (``tensor.data_ptr()``), streams as ``cudaStream_t``.
+
+The product path has no CPU fallback: if the library is missing or cannot be loaded,
+`load()` raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libdreamzs.so')
+
+ABI_VERSION = 1
+OK, E_BADARG, E_LAUNCH, E_UNSUPPORTED = 0, -1, -2, -3
+MAX_NCR, MAX_NGAMMA, MAX_DEPAIRS, MAX_MULTITRY, MAX_NDIM = 16, 8, 8, 16, 1024
+FLAG_ALL_FLAT = 1
+PRIOR_FLAT, PRIOR_NORMAL, PRIOR_UNIFORM = 0, 1, 2
+
+EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_adapt_workspace_bytes',
+           'dreamzs_adapt_colsum', 'dreamzs_adapt_colsq', 'dreamzs_adapt_jumps', 'dreamzs_adapt_finish',
+           'dreamzs_gr_chain_stats', 'dreamzs_gr_finish']
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        'abi_version', 'ndim', 'ld', 'nchains_global', 'chain_begin', 'nchains_local', 'nCR', 'ngamma', 'nDEpairs',
+        'multitry', 'hardboundaries', 'history_thin', 'target_kind', 'flags')] + [
+        ('snooker', C.c_double), ('p_gamma_unity', C.c_double), ('lamb', C.c_double), ('zeta', C.c_double),
+        ('seed', C.c_uint64)]
+
+
+class State(C.Structure):
+    _fields_ = [('Z', C.c_void_p), ('Z_capacity_rows', C.c_int64), ('X', C.c_void_p), ('last_prior', C.c_void_p),
+                ('last_like', C.c_void_p), ('cr_probs', C.c_void_p), ('gamma_probs', C.c_void_p),
+                ('gamma_table', C.c_void_p), ('target_table', C.c_void_p), ('prior_kind', C.c_void_p),
+                ('prior_a', C.c_void_p), ('prior_b', C.c_void_p), ('mins', C.c_void_p), ('maxs', C.c_void_p)]
+
+
+class Trace(C.Structure):
+    _fields_ = [('trace', C.c_void_p), ('trace_logp', C.c_void_p), ('decisions', C.c_void_p),
+                ('trace_iters', C.c_int64), ('trace_offset', C.c_int64)]
+
+
+class DreamzsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libdreamzs.so (built in-tree by pydream_b200.build).  Raises if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DreamzsError('libdreamzs.so not found at %s: build it with `python -m pydream_b200.build` '
+                           '(there is no CPU fallback for the MT-DREAM(ZS) step path)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    cfgp, stp, trp = C.POINTER(Config), C.POINTER(State), C.POINTER(Trace)
+    sig = {
+        'dreamzs_abi_version': (C.c_int, []),
+        'dreamzs_init_logp': (C.c_int, [cfgp, stp, vp]),
+        'dreamzs_step': (C.c_int, [cfgp, stp, trp, i64, i32, i64, vp]),
+        'dreamzs_adapt_workspace_bytes': (i64, [cfgp]),
+        'dreamzs_adapt_colsum': (C.c_int, [cfgp, vp, vp, vp, vp]),
+        'dreamzs_adapt_colsq': (C.c_int, [cfgp, vp, vp, vp, vp, vp]),
+        'dreamzs_adapt_jumps': (C.c_int, [cfgp, vp, vp, i64, vp, i64, vp, i32, i32, i32, vp, vp, vp]),
+        'dreamzs_adapt_finish': (C.c_int, [cfgp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+        'dreamzs_gr_chain_stats': (C.c_int, [vp, i64, i64, i64, i32, i64, vp, vp, vp]),
+        'dreamzs_gr_finish': (C.c_int, [vp, vp, i64, i64, i32, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.dreamzs_abi_version() != ABI_VERSION:
+        raise DreamzsError('libdreamzs.so ABI version %d != %d' % (lib.dreamzs_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+_ERR = {E_BADARG: 'bad argument', E_LAUNCH: 'CUDA launch failure', E_UNSUPPORTED: 'unsupported option combination'}
+
+
+def check(rc, what):
+    if rc != OK:
+        raise DreamzsError('%s failed: %s (%d)' % (what, _ERR.get(rc, 'unknown error'), rc))

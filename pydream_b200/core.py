@@ -1,0 +1,173 @@
+"""``run_dream``: drop-in for pydream.core.run_dream (pydream/core.py:11-86) on one or more B200s.
+
+Same signature, keyword names, defaults, checks, exception texts and return shapes as the
+reference.  The multiprocessing pool (core.py:250-327) is replaced by `engine.DreamEngine`: all
+chains advance in lock-step inside one fused sm_100a kernel.  Extra, optional keywords (not in the
+reference): ``seed`` (Philox key; default drawn from the OS like the reference's unseeded runs),
+``device``, ``group`` (torch.distributed process group: chains are sharded over its ranks and each
+rank returns the chains it owns), ``return_device`` (return device tensors instead of numpy lists).
+"""
+import os
+from datetime import datetime
+
+import numpy as np
+
+from .Dream import Dream
+from .model import Model
+from . import targets as T
+
+
+def _prior_arrays(parameters):
+    kinds, a, b = [], [], []
+    for p in parameters:
+        cf = p.closed_form() if hasattr(p, 'closed_form') else None
+        if cf is None:
+            raise NotImplementedError(
+                'pydream_b200 evaluates FlatParam, scipy.stats.norm and scipy.stats.uniform priors in-kernel; '
+                'prior %r has no closed form here' % (p,))
+        k, loc, scale = cf
+        kinds.append(np.full(p.dsize, k, dtype=np.int32))
+        a.append(loc)
+        b.append(scale)
+    return np.concatenate(kinds), np.concatenate(a), np.concatenate(b)
+
+
+def _reference_archive_rows(nchains, niterations, step, len_old_history):
+    """Archive sizing of _setup_mp_dream_pool (pydream/core.py:260-268), in rows."""
+    d, thin = step.total_var_dimension, step.history_thin
+    seed_len = len_old_history if step.history_file != False else step.nseedchains * d   # noqa: E712
+    if niterations < thin:
+        arr_dim = ((np.floor(nchains*niterations/thin)+nchains)*d)+seed_len
+    else:
+        arr_dim = np.floor(((nchains*niterations*d)/thin))+seed_len
+    return int(arr_dim) // d
+
+
+def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, restart=False, verbose=True,
+              nverbose=10, tempering=False, mp_context=None, **kwargs):
+    """Run MT-DREAM(ZS); returns (sampled_params, log_ps): per chain an (niterations, ndim) array and an
+    (niterations, 1) array, as pydream.core.run_dream does."""
+    seed = kwargs.pop('seed', None)
+    device = kwargs.pop('device', None)
+    group = kwargs.pop('group', None)
+    return_device = kwargs.pop('return_device', False)
+
+    if restart:
+        if start == None:   # noqa: E711
+            raise Exception('Restart run specified but no start positions given.')
+        if 'model_name' not in kwargs:
+            raise Exception('Restart run specified but no model name to load history and crossover value files from given.')
+    if type(parameters) is not list:
+        parameters = [parameters]
+    model = Model(likelihood=likelihood, sampled_parameters=parameters)
+    if restart:
+        step_instance = Dream(model=model, variables=parameters,
+                              history_file=kwargs['model_name'] + '_DREAM_chain_history.npy',
+                              crossover_file=kwargs['model_name'] + '_DREAM_chain_adapted_crossoverprob.npy',
+                              gamma_file=kwargs['model_name'] + '_DREAM_chain_adapted_gammalevelprob.npy',
+                              verbose=verbose, mp_context=mp_context, **kwargs)
+    else:
+        step_instance = Dream(model=model, variables=parameters, verbose=verbose, mp_context=mp_context, **kwargs)
+    if tempering:
+        raise NotImplementedError('parallel tempering (pydream/core.py:131-248, "untested" in the reference) is outside '
+                                  'the accelerated step path')
+
+    d = step_instance.total_var_dimension
+    # ---- checks and sizing of _setup_mp_dream_pool (pydream/core.py:250-305), same messages
+    min_njobs = (2*len(step_instance.DEpairs))+1
+    if nchains < min_njobs:
+        raise Exception('Dream should be run with at least (2*DEpairs)+1 number of chains.  For current algorithmic settings, set njobs>=%s.' % str(min_njobs))
+    old_history = None
+    len_old_history = 0
+    if step_instance.history_file != False:   # noqa: E712
+        old_history = np.load(step_instance.history_file)
+        len_old_history = len(old_history.flatten())
+        step_instance.nseedchains = len_old_history/d
+    min_nseedchains = 2*len(step_instance.DEpairs)*nchains
+    if step_instance.nseedchains < min_nseedchains:
+        raise Exception('The size of the seeded starting history is insufficient.  Increase nseedchains>=%s.' % str(min_nseedchains))
+    if step_instance.crossover_burnin == None:   # noqa: E711
+        step_instance.crossover_burnin = int(np.floor(niterations/10))
+    if start is not None:
+        if step_instance.start_random:
+            print('Warning: start position provided but random_start set to True.  Overrode random_start value and starting walk at provided start position.')
+            step_instance.start_random = False
+
+    if not isinstance(likelihood, T.AnalyticTarget):
+        raise NotImplementedError(
+            'pydream_b200 runs the whole step on the GPU and needs an analytic target from pydream_b200.targets '
+            '(CorrelatedGaussian, BimodalMixture, Banana, SumShift, Constant); arbitrary Python likelihoods are '
+            'not evaluated on the host (no CPU fallback)')
+    if likelihood.ndim != d:
+        raise ValueError('target dimension %d != total parameter dimension %d' % (likelihood.ndim, d))
+    prior_kind, prior_a, prior_b = _prior_arrays(parameters)
+
+    # ---- archive seed (Dream.py:203-214) and start positions (core.py:74-78, Dream.py:221-225)
+    if old_history is not None:
+        history = np.asarray(old_history, dtype=np.float64).reshape(-1, d)
+    else:
+        nseed = int(step_instance.nseedchains)
+        history = np.array([step_instance.draw_from_prior(step_instance.variables) for _ in range(nseed)]).reshape(nseed, d)
+    if step_instance.start_random:
+        starts = np.array([step_instance.draw_from_prior(step_instance.variables, random_seed=True) for _ in range(nchains)])
+    elif type(start) is list:
+        starts = np.array([np.asarray(s, dtype=np.float64).reshape(-1) for s in start[:nchains]])
+    else:
+        starts = np.tile(np.asarray(start, dtype=np.float64).reshape(1, -1), (nchains, 1))
+    starts = starts.reshape(nchains, d)
+
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), 'little')
+
+    from .engine import DreamEngine   # imports torch; fails loudly without CUDA / libdreamzs.so
+    eng = DreamEngine(d, nchains, history, starts, likelihood, prior_kind, prior_a, prior_b, seed=seed,
+                      nCR=step_instance.nCR, gamma_levels=step_instance.ngamma, DEpairs=len(step_instance.DEpairs),
+                      multitry=int(step_instance.multitry), snooker=step_instance.snooker,
+                      p_gamma_unity=step_instance.p_gamma_unity, lamb=step_instance.lamb, zeta=step_instance.zeta,
+                      history_thin=step_instance.history_thin, hardboundaries=bool(step_instance.boundaries),
+                      adapt_crossover=step_instance.adapt_crossover, adapt_gamma=step_instance.adapt_gamma,
+                      crossover_burnin=step_instance.crossover_burnin,
+                      cr_probs=np.asarray(step_instance.CR_probabilities, dtype=np.float64),
+                      gamma_probs=np.asarray(step_instance.gamma_probabilities, dtype=np.float64),
+                      device=device, group=group, record_decisions=bool(verbose))
+    trace, logp, dec = eng.run(niterations)
+    step_instance.CR_probabilities = eng.cr_probs.cpu().numpy()
+    step_instance.gamma_probabilities = eng.gamma_probs.cpu().numpy()
+
+    if verbose and dec is not None:
+        _print_acceptance(dec, niterations, nverbose)
+
+    # ---- history / adapted probabilities on disk when the archive is full (Dream.py:939-969)
+    if step_instance.save_history and eng.rank == 0:
+        ref_rows = _reference_archive_rows(nchains, niterations, step_instance, len_old_history)
+        if eng.archive_rows >= ref_rows:
+            prefix = (step_instance.model_name + '_') if step_instance.model_name else datetime.now().strftime('%Y_%m_%d_%H:%M:%S') + '_'
+            step_instance.save_history_to_disc(eng.history_flat()[:ref_rows * d], prefix)
+
+    if return_device:
+        return trace, logp
+    import torch
+    tr_host = torch.empty((eng.Nl, niterations, d), dtype=torch.float64, pin_memory=True)
+    lp_host = torch.empty((eng.Nl, niterations, 1), dtype=torch.float64, pin_memory=True)
+    tr_host.copy_(trace[:, :, :d], non_blocking=True)
+    lp_host.copy_(logp.unsqueeze(2), non_blocking=True)
+    torch.cuda.current_stream(eng.device).synchronize()
+    tr_np, lp_np = tr_host.numpy(), lp_host.numpy()
+    sampled_params = [tr_np[c] for c in range(eng.Nl)]
+    log_ps = [lp_np[c] for c in range(eng.Nl)]
+    return sampled_params, log_ps
+
+
+def _print_acceptance(dec, niterations, nverbose):
+    """Acceptance-rate lines at the cadence of _sample_dream (pydream/core.py:104-112), averaged over chains
+    (the reference prints one line per chain process)."""
+    import torch
+    acc = (dec & 1).to(torch.float64)               # [Nl, T]
+    cum = torch.cumsum(acc.mean(dim=0), dim=0).cpu().numpy()
+    for iteration in range(0, niterations, max(int(nverbose), 1)):
+        naccepts = cum[iteration - 1] if iteration > 0 else 0.0
+        print('Iteration: ', iteration, ' acceptance rate: ', float(naccepts)/(iteration+1))
+        if iteration % 100 == 0:
+            lo = cum[iteration - 101] if iteration > 100 else 0.0
+            win = (naccepts - lo) if iteration > 0 else 0.0
+            print('Iteration: ', iteration, ' acceptance rate over last 100 iterations: ', float(win)/100)

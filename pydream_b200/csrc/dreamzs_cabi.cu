@@ -1,0 +1,90 @@
+// extern "C" entry points of libdreamzs.so for the fused step (include/dreamzs.h) and the
+// dispatch over the <G, R> kernel instantiations (one object file each, dreamzs_step_inst.cu).
+#include "dreamzs_step_params.cuh"
+
+using namespace dreamzs;
+
+#define DZ_DECL(g, r) int dreamzs_launch_step_##g##_##r(const dreamzs::StepParams &, int, size_t, cudaStream_t);
+DZ_DECL(4, 1) DZ_DECL(8, 1) DZ_DECL(16, 1) DZ_DECL(32, 1) DZ_DECL(32, 2) DZ_DECL(32, 4) DZ_DECL(32, 8)
+#undef DZ_DECL
+
+static int table_doubles_of(const dreamzs_config *cfg) {
+  const int d = cfg->ndim;
+  switch (cfg->target_kind) {
+    case DREAMZS_TARGET_CONSTANT: case DREAMZS_TARGET_SUMSHIFT: return 1;
+    case DREAMZS_TARGET_GAUSSIAN_DENSE: return 2 + cfg->ld * d;   // [log_F, 0, invC^T rows padded to ld]
+    case DREAMZS_TARGET_MIXTURE: return 2 + 2 * d;
+    case DREAMZS_TARGET_BANANA: return 2;
+    default: return -1;
+  }
+}
+
+static int check_cfg(const dreamzs_config *cfg, const dreamzs_state *st) {
+  if (!cfg || !st || cfg->abi_version != DREAMZS_ABI_VERSION) return DREAMZS_E_BADARG;
+  if (cfg->ndim < 1 || cfg->ndim > DREAMZS_MAX_NDIM || cfg->ld < cfg->ndim || (cfg->ld & 3)) return DREAMZS_E_BADARG;
+  if (cfg->nchains_local < 0 || cfg->chain_begin < 0 || cfg->chain_begin + cfg->nchains_local > cfg->nchains_global) return DREAMZS_E_BADARG;
+  if (cfg->nCR < 1 || cfg->nCR > DREAMZS_MAX_NCR || cfg->ngamma < 1 || cfg->ngamma > DREAMZS_MAX_NGAMMA) return DREAMZS_E_BADARG;
+  if (cfg->nDEpairs < 1 || cfg->nDEpairs > DREAMZS_MAX_DEPAIRS) return DREAMZS_E_BADARG;
+  if (cfg->multitry < 1 || 2 * cfg->multitry > DREAMZS_MAX_MULTITRY) return DREAMZS_E_BADARG;
+  if (cfg->multitry == 2) return DREAMZS_E_UNSUPPORTED;   // broken in the reference too (Dream.py:867-868)
+  if (cfg->history_thin < 1) return DREAMZS_E_BADARG;
+  if (!st->Z || !st->X || !st->last_prior || !st->last_like || !st->cr_probs || !st->gamma_probs || !st->gamma_table ||
+      !st->target_table || !st->prior_kind || !st->prior_a || !st->prior_b || !st->mins || !st->maxs)
+    return DREAMZS_E_BADARG;
+  return DREAMZS_OK;
+}
+
+static int dispatch(StepParams &P, cudaStream_t stream) {
+  const dreamzs_config &cfg = P.cfg;
+  const int chunks = cfg.ld / 4;
+  P.table_doubles = table_doubles_of(&cfg);
+  if (P.table_doubles < 0) return DREAMZS_E_UNSUPPORTED;
+  P.nslots = cfg.multitry == 1 ? 1 : cfg.multitry + 1;
+  const int threads = 128;
+  int G = 32, R = 1;
+  if (chunks <= 4) G = 4; else if (chunks <= 8) G = 8; else if (chunks <= 16) G = 16;
+  else { R = (chunks + 31) / 32; if (R > 2 && R <= 4) R = 4; else if (R > 4) R = 8; }
+  const int chains_per_cta = (threads / 32) * (32 / G);
+  const size_t chain_bytes = (size_t)chains_per_cta * ((size_t)P.nslots * cfg.ld + 3 * DREAMZS_MAX_MULTITRY) * sizeof(double);
+  const size_t table_bytes = (size_t)((P.table_doubles + 1) & ~1) * sizeof(double);
+  P.table_in_smem = (table_bytes + chain_bytes <= 200 * 1024) ? 1 : 0;
+  const size_t smem = chain_bytes + (P.table_in_smem ? table_bytes : 0);
+  if (smem > 227 * 1024) return DREAMZS_E_UNSUPPORTED;
+#define DZ_CASE(g, r) if (G == g && R == r) return dreamzs_launch_step_##g##_##r(P, threads, smem, stream);
+  DZ_CASE(4, 1) DZ_CASE(8, 1) DZ_CASE(16, 1) DZ_CASE(32, 1) DZ_CASE(32, 2) DZ_CASE(32, 4) DZ_CASE(32, 8)
+#undef DZ_CASE
+  return DREAMZS_E_UNSUPPORTED;
+}
+
+static int all_flat_hint(const dreamzs_config *cfg) { return cfg->flags & DREAMZS_FLAG_ALL_FLAT; }
+
+extern "C" int dreamzs_abi_version(void) { return DREAMZS_ABI_VERSION; }
+
+extern "C" int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state *st, void *stream) {
+  int rc = check_cfg(cfg, st);
+  if (rc != DREAMZS_OK) return rc;
+  if (cfg->nchains_local == 0) return DREAMZS_OK;
+  StepParams P{};
+  P.cfg = *cfg; P.st = *st; P.init_only = 1; P.all_flat = all_flat_hint(cfg);
+  return dispatch(P, (cudaStream_t)stream);
+}
+
+extern "C" int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
+                            int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream) {
+  int rc = check_cfg(cfg, st);
+  if (rc != DREAMZS_OK) return rc;
+  if (!tr || !tr->trace || !tr->trace_logp || niter < 0 || iter_begin < 0) return DREAMZS_E_BADARG;
+  if (tr->trace_offset < 0 || tr->trace_offset + niter > tr->trace_iters) return DREAMZS_E_BADARG;
+  if (archive_rows < 2 * cfg->nDEpairs || archive_rows > st->Z_capacity_rows) return DREAMZS_E_BADARG;
+  // only the last iteration of a launch may append (the archive is read-only inside a launch)
+  for (int it = 0; it + 1 < niter; ++it)
+    if ((iter_begin + it) % cfg->history_thin == 0) return DREAMZS_E_BADARG;
+  if (niter > 0 && (iter_begin + niter - 1) % cfg->history_thin == 0 &&
+      archive_rows + cfg->nchains_global > st->Z_capacity_rows)
+    return DREAMZS_E_BADARG;
+  if (niter == 0 || cfg->nchains_local == 0) return DREAMZS_OK;
+  StepParams P{};
+  P.cfg = *cfg; P.st = *st; P.tr = *tr; P.iter_begin = iter_begin; P.niter = niter; P.archive_rows = archive_rows;
+  P.all_flat = all_flat_hint(cfg);
+  return dispatch(P, (cudaStream_t)stream);
+}

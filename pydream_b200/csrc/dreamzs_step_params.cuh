@@ -1,0 +1,21 @@
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/dreamzs.h"
+
+namespace dreamzs {
+
+struct StepParams {
+  dreamzs_config cfg;
+  dreamzs_state st;
+  dreamzs_trace tr;
+  int64_t iter_begin;
+  int32_t niter;
+  int64_t archive_rows;
+  int32_t all_flat;       // every prior is FLAT (skip prior evaluation and bounds)
+  int32_t table_in_smem;  // target table staged in shared memory
+  int32_t table_doubles;  // length of the target table
+  int32_t nslots;         // proposal slots per chain in shared memory
+  int32_t init_only;      // dreamzs_init_logp: evaluate logp(X) and return
+};
+
+}  // namespace dreamzs

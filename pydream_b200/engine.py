@@ -1,0 +1,273 @@
+"""Device-resident MT-DREAM(ZS) engine: owns the HBM state and schedules the sm_100a kernels.
+
+Replaces, for analytic targets, the reference's process pool + shared-memory namespace
+(pydream/core.py:66-129, 250-327; pydream/Dream_shared_vars.py): every chain is a lane-group of
+one fused kernel, the archive ``Z`` lives in HBM, and the chain loop of ``_sample_dream`` becomes
+a sequence of launches of up to ``history_thin`` fused iterations (the archive is immutable inside
+such a window).  PyTorch is used only for device memory, streams and ``torch.distributed``.
+
+Data layout in HBM (all float64, row stride ``ld`` = ndim rounded up to 4 doubles = 32 B):
+    Z      [capacity_rows, ld]   archive, seed rows first, then N rows per append in chain order
+    X      [N_local, ld]         current positions
+    trace  [N_local, T, ld]      sampled_params (chain-major: chain c's trace is contiguous)
+    logp   [N_local, T]          log_ps
+    dec    [N_local, T] uint32   decision words (accept / snooker / CR / gamma level / multi-try pick)
+Sharding: rank r owns global chains [r*N/G, (r+1)*N/G); Z is replicated; after every appending
+launch the new rows are all-gathered in place over NCCL (NVLink/NVSwitch) straight into Z's tail.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import targets as T
+
+
+def round_up4(d):
+    return (int(d) + 3) // 4 * 4
+
+
+def gamma_table(ngamma, nDEpairs, ndim):
+    """Dream.gamma_arr (pydream/Dream.py:173-179), computed with numpy exactly as the reference does."""
+    gamma_array = np.zeros((ngamma, nDEpairs, ndim))
+    gamma_level_decrease = 1
+    for gamma_level in range(1, ngamma + 1):
+        for delta in range(1, nDEpairs + 1):
+            gamma_array[gamma_level - 1, delta - 1, :] = (2.38 / np.sqrt(2 * delta * np.linspace(1, ndim, num=ndim))) / gamma_level_decrease
+        gamma_level_decrease = gamma_level_decrease * 2
+    return gamma_array
+
+
+def device_target_table(target, ld):
+    """Flat float64 table in the layout the kernels expect (include/dreamzs.h dreamzs_target_kind)."""
+    if target.kind == T.TARGET_GAUSSIAN_DENSE:
+        d = target.ndim
+        At = np.zeros((d, ld))
+        At[:, :d] = target.invC.T
+        return np.concatenate([[target.log_F, 0.0], At.reshape(-1)])
+    return np.ascontiguousarray(target.table(), dtype=np.float64)
+
+
+def appends_in(iter_begin, niter, thin):
+    """Number of iterations t in [iter_begin, iter_begin+niter) with t % thin == 0."""
+    if niter <= 0:
+        return 0
+    first = ((iter_begin + thin - 1) // thin) * thin
+    last = iter_begin + niter - 1
+    return 0 if first > last else (last - first) // thin + 1
+
+
+def plan_segments(iter_begin, niter, thin, single_until):
+    """Split [iter_begin, iter_begin+niter) into launches: a launch ends at an appending iteration
+    (t % thin == 0) and iterations t <= single_until run one per launch (burn-in adaptation)."""
+    segs = []
+    t, end = iter_begin, iter_begin + niter
+    while t < end:
+        if t <= single_until:
+            n = 1
+        else:
+            nxt = ((t + thin - 1) // thin) * thin   # first appending iteration >= t
+            n = min(end, nxt + 1) - t
+        segs.append((t, n))
+        t += n
+    return segs
+
+
+class DreamEngine:
+    def __init__(self, ndim, nchains, history, starts, target, prior_kind=None, prior_a=None, prior_b=None, seed=0,
+                 nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
+                 history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
+                 cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True):
+        if not torch.cuda.is_available():
+            raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.lib = _cabi.load()
+        self.group = group
+        self.world = torch.distributed.get_world_size(group) if group is not None else 1
+        self.rank = torch.distributed.get_rank(group) if group is not None else 0
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        d, N = int(ndim), int(nchains)
+        if N % self.world:
+            raise ValueError('nchains (%d) must be divisible by the number of GPUs (%d)' % (N, self.world))
+        self.d, self.N, self.ld = d, N, round_up4(d)
+        self.Nl = N // self.world
+        self.c0 = self.rank * self.Nl
+        self.thin = int(history_thin)
+        self.adapt_crossover, self.adapt_gamma = bool(adapt_crossover), bool(adapt_gamma)
+        self.crossover_burnin = int(crossover_burnin)
+        self.record_decisions = bool(record_decisions) or self.adapt_crossover or self.adapt_gamma
+        self.target = target
+        f64 = dict(dtype=torch.float64, device=self.device)
+        history = np.asarray(history, dtype=np.float64).reshape(-1, d)
+        self.nseed = history.shape[0]
+        self.count = 0
+        self.iter = 0
+        self._hist_host = history
+        self.Z = None
+        self._ensure_capacity(self.nseed)
+        starts = np.asarray(starts, dtype=np.float64).reshape(N, d)
+        Xh = np.zeros((self.Nl, self.ld))
+        Xh[:, :d] = starts[self.c0:self.c0 + self.Nl]
+        self.X = torch.from_numpy(Xh).to(self.device)
+        self.last_prior = torch.zeros(self.Nl, **f64)
+        self.last_like = torch.zeros(self.Nl, **f64)
+        pk = np.zeros(d, dtype=np.int32) if prior_kind is None else np.ascontiguousarray(prior_kind, dtype=np.int32)
+        pa = np.zeros(d) if prior_a is None else np.ascontiguousarray(prior_a, dtype=np.float64)
+        pb = np.ones(d) if prior_b is None else np.ascontiguousarray(prior_b, dtype=np.float64)
+        mins, maxs = np.full(d, -np.inf), np.full(d, np.inf)
+        u = pk == _cabi.PRIOR_UNIFORM
+        mins[u], maxs[u] = pa[u], pa[u] + pb[u]
+        self.all_flat = bool(np.all(pk == _cabi.PRIOR_FLAT))
+        self.prior_kind = torch.from_numpy(pk).to(self.device)
+        self.prior_a, self.prior_b = torch.from_numpy(pa).to(self.device), torch.from_numpy(pb).to(self.device)
+        self.mins, self.maxs = torch.from_numpy(mins).to(self.device), torch.from_numpy(maxs).to(self.device)
+        crp = np.array(cr_probs if cr_probs is not None else [1 / float(nCR)] * nCR, dtype=np.float64)
+        gpr = np.array(gamma_probs if gamma_probs is not None else [1 / float(gamma_levels)] * gamma_levels, dtype=np.float64)
+        self.cr_probs, self.gamma_probs = torch.from_numpy(crp).to(self.device), torch.from_numpy(gpr).to(self.device)
+        self.ncr_updates, self.delta_m = torch.zeros(nCR, **f64), torch.zeros(nCR, **f64)
+        self.ngamma_updates, self.delta_m_gamma = torch.zeros(gamma_levels, **f64), torch.zeros(gamma_levels, **f64)
+        self.gamma_table = torch.from_numpy(gamma_table(gamma_levels, DEpairs, d)).to(self.device)
+        self.target_table = torch.from_numpy(device_target_table(target, self.ld)).to(self.device)
+        self.cfg = _cabi.Config(abi_version=_cabi.ABI_VERSION, ndim=d, ld=self.ld, nchains_global=N, chain_begin=self.c0,
+                                nchains_local=self.Nl, nCR=nCR, ngamma=gamma_levels, nDEpairs=DEpairs, multitry=multitry,
+                                hardboundaries=int(bool(hardboundaries)), history_thin=self.thin,
+                                target_kind=int(target.kind), flags=_cabi.FLAG_ALL_FLAT if self.all_flat else 0,
+                                snooker=snooker, p_gamma_unity=p_gamma_unity, lamb=lamb, zeta=zeta, seed=int(seed) & (2 ** 64 - 1))
+        ws = self.lib.dreamzs_adapt_workspace_bytes(C.byref(self.cfg))
+        self.workspace = torch.zeros(max(int(ws), 8) // 8 + 1, **f64)
+        self.colsum, self.colsq = torch.zeros(d, **f64), torch.zeros(d, **f64)
+        self.partial = torch.zeros(2 * nCR + 2 * gamma_levels, **f64)
+        self.launches = 0
+        self._state()
+        _cabi.check(self.lib.dreamzs_init_logp(C.byref(self.cfg), C.byref(self.st), self._stream()), 'dreamzs_init_logp')
+        self.launches += 1
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _state(self):
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self.st = _cabi.State(Z=p(self.Z), Z_capacity_rows=self.Z.shape[0], X=p(self.X), last_prior=p(self.last_prior),
+                              last_like=p(self.last_like), cr_probs=p(self.cr_probs), gamma_probs=p(self.gamma_probs),
+                              gamma_table=p(self.gamma_table), target_table=p(self.target_table),
+                              prior_kind=p(self.prior_kind), prior_a=p(self.prior_a), prior_b=p(self.prior_b),
+                              mins=p(self.mins), maxs=p(self.maxs))
+
+    def _ensure_capacity(self, rows):
+        if self.Z is not None and self.Z.shape[0] >= rows:
+            return
+        Z = torch.zeros((rows, self.ld), dtype=torch.float64, device=self.device)
+        if self.Z is None:
+            h = np.zeros((self.nseed, self.ld))
+            h[:, :self.d] = self._hist_host
+            Z[:self.nseed] = torch.from_numpy(h).to(self.device)
+        else:
+            Z[:self.Z.shape[0]] = self.Z
+        self.Z = Z
+        if hasattr(self, 'st'):
+            self._state()
+
+    @property
+    def archive_rows(self):
+        return self.nseed + self.count
+
+    # ------------------------------------------------------------------ sampling
+    def run(self, niter, trace=None, logp=None, decisions=None):
+        """Run `niter` iterations for the local chains.  Returns (trace [Nl,niter,ld], logp [Nl,niter],
+        decisions [Nl,niter] or None) as device tensors (stream-ordered, not synchronised)."""
+        niter = int(niter)
+        dev = self.device
+        if trace is None:
+            trace = torch.empty((self.Nl, niter, self.ld), dtype=torch.float64, device=dev)
+        if logp is None:
+            logp = torch.empty((self.Nl, niter), dtype=torch.float64, device=dev)
+        if decisions is None and self.record_decisions:
+            decisions = torch.empty((self.Nl, niter), dtype=torch.int32, device=dev)
+        self._ensure_capacity(self.archive_rows + appends_in(self.iter, niter, self.thin) * self.N)
+        adapting = self.adapt_crossover or self.adapt_gamma
+        single_until = self.crossover_burnin if adapting else -1
+        tr = _cabi.Trace(trace=trace.data_ptr(), trace_logp=logp.data_ptr(),
+                         decisions=decisions.data_ptr() if decisions is not None else None, trace_iters=niter, trace_offset=0)
+        t_first = self.iter
+        stream = self._stream()
+        cfg, st = C.byref(self.cfg), C.byref(self.st)
+        for (t, n) in plan_segments(self.iter, niter, self.thin, single_until):
+            tr.trace_offset = t - t_first
+            rc = self.lib.dreamzs_step(cfg, st, C.byref(tr), t, n, self.archive_rows, stream)
+            _cabi.check(rc, 'dreamzs_step')
+            self.launches += 1
+            last = t + n - 1
+            if adapting and n == 1 and ((10 < last < self.crossover_burnin) or last == self.crossover_burnin):
+                self._adapt(trace, decisions, last - t_first, last == self.crossover_burnin)
+            if last % self.thin == 0:
+                self._publish_append()
+        self.iter += niter
+        return trace, logp, decisions
+
+    def _publish_append(self):
+        """record_history for the whole sweep: the kernel wrote the local rows; gather the others."""
+        M = self.archive_rows
+        if self.world > 1:
+            block = self.Z[M:M + self.N]
+            mine = block[self.c0:self.c0 + self.Nl]
+            torch.distributed.all_gather_into_tensor(block.view(-1), mine.reshape(-1), group=self.group)
+        self.count += self.N
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.group)
+
+    def _adapt(self, trace, decisions, trow, final):
+        """One sweep of estimate_crossover_probabilities / estimate_gamma_level_probs (Dream.py:451-540)."""
+        lib, cfg, s = self.lib, C.byref(self.cfg), self._stream()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        T_ = trace.shape[1]
+        if trow == 0:
+            raise _cabi.DreamzsError('adaptation needs the previous state in the trace')
+        x_old = C.c_void_p(trace.data_ptr() + (trow - 1) * self.ld * 8)
+        dec = C.c_void_p(decisions.data_ptr() + trow * 4)
+        _cabi.check(lib.dreamzs_adapt_colsum(cfg, p(self.X), p(self.colsum), p(self.workspace), s), 'dreamzs_adapt_colsum')
+        self._allreduce(self.colsum)
+        _cabi.check(lib.dreamzs_adapt_colsq(cfg, p(self.X), p(self.colsum), p(self.colsq), p(self.workspace), s), 'dreamzs_adapt_colsq')
+        self._allreduce(self.colsq)
+        _cabi.check(lib.dreamzs_adapt_jumps(cfg, p(self.X), x_old, T_ * self.ld, dec, T_, p(self.colsq), int(final),
+                                            int(self.adapt_crossover), int(self.adapt_gamma), p(self.partial),
+                                            p(self.workspace), s), 'dreamzs_adapt_jumps')
+        self._allreduce(self.partial)
+        _cabi.check(lib.dreamzs_adapt_finish(cfg, p(self.partial), int(self.adapt_crossover), int(self.adapt_gamma),
+                                             p(self.ncr_updates), p(self.delta_m), p(self.cr_probs), p(self.ngamma_updates),
+                                             p(self.delta_m_gamma), p(self.gamma_probs), s), 'dreamzs_adapt_finish')
+        self.launches += 7
+
+    # ------------------------------------------------------------------ diagnostics / export
+    def gelman_rubin(self, trace):
+        """Gelman_Rubin (pydream/convergence.py:3-20) of a device trace [Nl, T, ld] -> Rhat[d] (device)."""
+        return gelman_rubin_device(trace, self.d, self.group)
+
+    def history_flat(self):
+        """The archive in the reference's on-disk layout: flat float64, rows of ndim (Dream.py:919-945)."""
+        n = self.archive_rows
+        return self.Z[:n, :self.d].contiguous().reshape(-1).cpu().numpy()
+
+
+def gelman_rubin_device(trace, ndim, group=None):
+    lib = _cabi.load()
+    Nl, T_, ld = trace.shape
+    dev = trace.device
+    mean = torch.empty((Nl, ndim), dtype=torch.float64, device=dev)
+    var = torch.empty((Nl, ndim), dtype=torch.float64, device=dev)
+    s = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _cabi.check(lib.dreamzs_gr_chain_stats(p(trace), Nl, T_, T_ // 2, ndim, ld, p(mean), p(var), s), 'dreamzs_gr_chain_stats')
+    if group is not None and torch.distributed.get_world_size(group) > 1:
+        W = torch.distributed.get_world_size(group)
+        gm = torch.empty((W * Nl, ndim), dtype=torch.float64, device=dev)
+        gv = torch.empty((W * Nl, ndim), dtype=torch.float64, device=dev)
+        torch.distributed.all_gather_into_tensor(gm.view(-1), mean.view(-1), group=group)
+        torch.distributed.all_gather_into_tensor(gv.view(-1), var.view(-1), group=group)
+        mean, var = gm, gv
+    rhat = torch.empty(ndim, dtype=torch.float64, device=dev)
+    _cabi.check(lib.dreamzs_gr_finish(p(mean), p(var), mean.shape[0], T_, ndim, p(rhat), s), 'dreamzs_gr_finish')
+    return rhat
