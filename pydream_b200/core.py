@@ -32,10 +32,15 @@ def _prior_arrays(parameters):
     return np.concatenate(kinds), np.concatenate(a), np.concatenate(b)
 
 
+def _has_history(step):
+    hf = step.history_file
+    return isinstance(hf, np.ndarray) or hf != False   # noqa: E712
+
+
 def _reference_archive_rows(nchains, niterations, step, len_old_history):
     """Archive sizing of _setup_mp_dream_pool (pydream/core.py:260-268), in rows."""
     d, thin = step.total_var_dimension, step.history_thin
-    seed_len = len_old_history if step.history_file != False else step.nseedchains * d   # noqa: E712
+    seed_len = len_old_history if _has_history(step) else step.nseedchains * d
     if niterations < thin:
         arr_dim = ((np.floor(nchains*niterations/thin)+nchains)*d)+seed_len
     else:
@@ -79,8 +84,10 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
         raise Exception('Dream should be run with at least (2*DEpairs)+1 number of chains.  For current algorithmic settings, set njobs>=%s.' % str(min_njobs))
     old_history = None
     len_old_history = 0
-    if step_instance.history_file != False:   # noqa: E712
-        old_history = np.load(step_instance.history_file)
+    if _has_history(step_instance):
+        # a path, as in the reference, or (extension) the array itself
+        hf = step_instance.history_file
+        old_history = hf if isinstance(hf, np.ndarray) else np.load(hf)
         len_old_history = len(old_history.flatten())
         step_instance.nseedchains = len_old_history/d
     min_nseedchains = 2*len(step_instance.DEpairs)*nchains

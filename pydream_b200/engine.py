@@ -23,6 +23,7 @@ import torch
 
 from . import _cabi
 from . import targets as T
+from .collectives import allgather_rows, allreduce_sum
 
 
 def round_up4(d):
@@ -187,6 +188,8 @@ class DreamEngine:
             decisions = torch.empty((self.Nl, niter), dtype=torch.int32, device=dev)
         self._ensure_capacity(self.archive_rows + appends_in(self.iter, niter, self.thin) * self.N)
         adapting = self.adapt_crossover or self.adapt_gamma
+        if adapting and self.iter <= self.crossover_burnin:
+            self._x_entry = self.X.clone()
         single_until = self.crossover_burnin if adapting else -1
         tr = _cabi.Trace(trace=trace.data_ptr(), trace_logp=logp.data_ptr(),
                          decisions=decisions.data_ptr() if decisions is not None else None, trace_iters=niter, trace_offset=0)
@@ -209,30 +212,27 @@ class DreamEngine:
     def _publish_append(self):
         """record_history for the whole sweep: the kernel wrote the local rows; gather the others."""
         M = self.archive_rows
-        if self.world > 1:
-            block = self.Z[M:M + self.N]
-            mine = block[self.c0:self.c0 + self.Nl]
-            torch.distributed.all_gather_into_tensor(block.view(-1), mine.reshape(-1), group=self.group)
+        allgather_rows(self.Z[M:M + self.N], self.c0, self.Nl, self.group)
         self.count += self.N
 
     def _allreduce(self, t):
-        if self.world > 1:
-            torch.distributed.all_reduce(t, group=self.group)
+        allreduce_sum(t, self.group)
 
     def _adapt(self, trace, decisions, trow, final):
         """One sweep of estimate_crossover_probabilities / estimate_gamma_level_probs (Dream.py:451-540)."""
         lib, cfg, s = self.lib, C.byref(self.cfg), self._stream()
         p = lambda t: C.c_void_p(t.data_ptr())
         T_ = trace.shape[1]
-        if trow == 0:
-            raise _cabi.DreamzsError('adaptation needs the previous state in the trace')
-        x_old = C.c_void_p(trace.data_ptr() + (trow - 1) * self.ld * 8)
+        if trow == 0:      # previous state is not in this call's trace: use the copy taken at run() entry
+            x_old, ld_old = p(self._x_entry), self.ld
+        else:
+            x_old, ld_old = C.c_void_p(trace.data_ptr() + (trow - 1) * self.ld * 8), T_ * self.ld
         dec = C.c_void_p(decisions.data_ptr() + trow * 4)
         _cabi.check(lib.dreamzs_adapt_colsum(cfg, p(self.X), p(self.colsum), p(self.workspace), s), 'dreamzs_adapt_colsum')
         self._allreduce(self.colsum)
         _cabi.check(lib.dreamzs_adapt_colsq(cfg, p(self.X), p(self.colsum), p(self.colsq), p(self.workspace), s), 'dreamzs_adapt_colsq')
         self._allreduce(self.colsq)
-        _cabi.check(lib.dreamzs_adapt_jumps(cfg, p(self.X), x_old, T_ * self.ld, dec, T_, p(self.colsq), int(final),
+        _cabi.check(lib.dreamzs_adapt_jumps(cfg, p(self.X), x_old, ld_old, dec, T_, p(self.colsq), int(final),
                                             int(self.adapt_crossover), int(self.adapt_gamma), p(self.partial),
                                             p(self.workspace), s), 'dreamzs_adapt_jumps')
         self._allreduce(self.partial)

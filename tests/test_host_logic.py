@@ -1,0 +1,130 @@
+"""CPU tests: the C ABI library loads and exports every symbol include/dreamzs.h declares (no compute
+calls), the launch planner, and the reference's argument checks / messages in run_dream
+(pydream/tests/test_dream.py:34-50)."""
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy.stats import norm, uniform
+
+from pydream_b200 import _cabi, targets
+from pydream_b200.core import run_dream
+from pydream_b200.Dream import Dream
+from pydream_b200.model import Model
+from pydream_b200.parameters import SampledParam, FlatParam
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'dreamzs.h')).read()
+    declared = set(re.findall(r'^(?:int|int64_t)\s+(dreamzs_\w+)\s*\(', hdr, flags=re.M))
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    lib = _cabi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dreamzs_abi_version() == _cabi.ABI_VERSION
+
+
+def test_struct_sizes_match_header():
+    import ctypes as C
+    assert C.sizeof(_cabi.Config) == 14 * 4 + 4 * 8 + 8
+    assert C.sizeof(_cabi.State) == 14 * 8
+    assert C.sizeof(_cabi.Trace) == 5 * 8
+
+
+def test_plan_segments():
+    from pydream_b200.engine import plan_segments, appends_in
+    segs = plan_segments(0, 25, 10, -1)
+    assert segs == [(0, 1), (1, 10), (11, 10), (21, 4)]
+    for t, n in segs:   # only the last iteration of a launch may append
+        assert all((t + i) % 10 != 0 for i in range(n - 1))
+    assert sum(n for _, n in segs) == 25
+    assert appends_in(0, 25, 10) == 3 and appends_in(1, 9, 10) == 0 and appends_in(1, 10, 10) == 1
+    segs = plan_segments(0, 30, 10, 12)   # burn-in: one iteration per launch up to iteration 12
+    assert segs[:13] == [(t, 1) for t in range(13)] and segs[13:] == [(13, 8), (21, 9)]
+    assert plan_segments(7, 5, 1, -1) == [(t, 1) for t in range(7, 12)]
+
+
+def onedmodel():
+    return [SampledParam(norm, loc=-2, scale=3)], targets.SumShift(1, 3.0)
+
+
+def multidmodel():
+    mu = np.array([-6.6, 3, 1.0, -.12])
+    sd = np.array([.13, 5, .9, 1.0])
+    return [SampledParam(norm, loc=mu, scale=sd)], targets.SumShift(4, 3.0)
+
+
+def test_fail_with_one_chain():
+    """pydream/tests/test_dream.py:34-38"""
+    param, like = onedmodel()
+    with pytest.raises(Exception, match='Dream should be run with at least '):
+        run_dream(param, like, nchains=1)
+
+
+def test_total_var_dimension_init():
+    """pydream/tests/test_dream.py:40-50"""
+    param, like = onedmodel()
+    step = Dream(model=Model(likelihood=like, sampled_parameters=param), variables=param)
+    assert step.total_var_dimension == 1
+    param, like = multidmodel()
+    step = Dream(model=Model(likelihood=like, sampled_parameters=param), variables=param)
+    assert step.total_var_dimension == 4
+
+
+def test_gamma_array():
+    """pydream/tests/test_dream.py:68-76"""
+    param, like = onedmodel()
+    step = Dream(model=Model(likelihood=like, sampled_parameters=param), DEpairs=5)
+    for d_prime, gamma_value in zip(range(1, 6), [1.683, 1.19, 0.972, 0.841, 0.753]):
+        assert round(abs(step.gamma_arr[0][d_prime - 1][0] - gamma_value), 3) == 0
+
+
+def test_restart_and_seed_checks():
+    param, like = multidmodel()
+    with pytest.raises(Exception, match='Restart run specified but no start positions given.'):
+        run_dream(param, like, nchains=3, restart=True)
+    with pytest.raises(Exception, match='no model name to load history'):
+        run_dream(param, like, nchains=3, restart=True, start=[np.zeros(4)] * 3)
+    with pytest.raises(Exception, match='The size of the seeded starting history is insufficient'):
+        run_dream(param, like, nchains=30, nseedchains=10)
+    with pytest.raises(Exception, match='not implemented yet'):
+        run_dream([FlatParam(test_value=np.zeros(4))], like, nchains=3, niterations=5)
+
+
+def test_dream_defaults_and_multitry_rules():
+    param, like = multidmodel()
+    m = Model(likelihood=like, sampled_parameters=param)
+    s = Dream(model=m)
+    assert (s.nCR, s.ngamma, s.multitry, s.snooker, s.p_gamma_unity, s.lamb, s.zeta, s.history_thin) == \
+        (3, 1, 1, .1, .2, .05, 1e-12, 10)
+    assert s.nseedchains == 40 and list(s.CR_values) == [1 / 3., 2 / 3., 1.0]
+    assert Dream(model=m, multitry=True).multitry == 5 and Dream(model=m, multitry=7).multitry == 7
+    assert Dream(model=m, nCR=9).nCR == 4          # clipped to the dimension, as the reference does
+    assert Dream(model=m, some_unknown_kwarg=1).extra_kwargs == {'some_unknown_kwarg': 1}
+
+
+def test_closed_form_priors():
+    p = SampledParam(uniform, loc=np.array([-5., 3.]), scale=np.array([15., 5.]))
+    k, a, b = p.closed_form()
+    assert k == 2 and list(a) == [-5., 3.] and list(b) == [15., 5.]
+    assert SampledParam(norm, loc=-2, scale=3).closed_form()[0] == 1
+    from scipy.stats import gamma
+    assert SampledParam(gamma, 2.0).closed_form() is None
+    x = np.array([0.5, 4.0])
+    assert np.isclose(Model(targets.SumShift(2), [p]).total_logp(x)[0], -np.log(15.) - np.log(5.))
+
+
+def test_targets_match_reference_example_formulas():
+    d = 6
+    g = targets.CorrelatedGaussian.benchmark(d)
+    A = .5 * np.identity(d) + .5 * np.ones((d, d))
+    Cm = np.array([[A[i][j] * np.sqrt((i + 1) * (j + 1)) for j in range(d)] for i in range(d)])
+    x = np.linspace(-1, 2, d)
+    ref = np.log(((2 * np.pi) ** (-d / 2)) * np.linalg.det(Cm) ** (-1. / 2)) - .5 * np.sum(x * np.dot(np.linalg.inv(Cm), x))
+    assert np.isclose(g(x), ref, rtol=1e-13)
+    mix = targets.BimodalMixture.benchmark(10)
+    x = np.full(10, 5.0)
+    assert np.isclose(mix(x), np.log(np.exp(-9.5949) + np.exp(-.5 * 1000 - 10.2880)))
