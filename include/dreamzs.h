@@ -47,6 +47,7 @@ extern "C" {
 
 /* dreamzs_config.flags */
 #define DREAMZS_FLAG_ALL_FLAT 1  /* every prior is FLAT: the kernels skip prior evaluation and bounds */
+#define DREAMZS_FLAG_GENERIC_KERNEL 2 /* always use the generic lane-group kernel (A/B testing of the specialised ones) */
 
 /* analytic log-likelihoods evaluated in-register (pydream_b200/targets.py) */
 enum dreamzs_target_kind {

@@ -14,6 +14,7 @@ ABI_VERSION = 1
 OK, E_BADARG, E_LAUNCH, E_UNSUPPORTED = 0, -1, -2, -3
 MAX_NCR, MAX_NGAMMA, MAX_DEPAIRS, MAX_MULTITRY, MAX_NDIM = 16, 8, 8, 16, 1024
 FLAG_ALL_FLAT = 1
+FLAG_GENERIC_KERNEL = 2
 PRIOR_FLAT, PRIOR_NORMAL, PRIOR_UNIFORM = 0, 1, 2
 
 EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_adapt_workspace_bytes',

@@ -7,6 +7,18 @@ using namespace dreamzs;
 #define DZ_DECL(g, r) int dreamzs_launch_step_##g##_##r(const dreamzs::StepParams &, int, size_t, cudaStream_t);
 DZ_DECL(4, 1) DZ_DECL(8, 1) DZ_DECL(16, 1) DZ_DECL(32, 1) DZ_DECL(32, 2) DZ_DECL(32, 4) DZ_DECL(32, 8)
 #undef DZ_DECL
+int dreamzs_launch_gauss_7(const dreamzs::StepParams &, cudaStream_t);
+int dreamzs_launch_gauss_8(const dreamzs::StepParams &, cudaStream_t);
+size_t dreamzs_launch_gauss_smem_bytes(const dreamzs_config &cfg, int TC);
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
 
 static int table_doubles_of(const dreamzs_config *cfg) {
   const int d = cfg->ndim;
@@ -40,6 +52,12 @@ static int dispatch(StepParams &P, cudaStream_t stream) {
   P.table_doubles = table_doubles_of(&cfg);
   if (P.table_doubles < 0) return DREAMZS_E_UNSUPPORTED;
   P.nslots = cfg.multitry == 1 ? 1 : cfg.multitry + 1;
+  // dense Gaussian, no multi-try, one warp-wide chunk row: CTA-synchronous kernel (dreamzs_gauss_kernel.cuh)
+  if (!P.init_only && cfg.target_kind == DREAMZS_TARGET_GAUSSIAN_DENSE && cfg.multitry == 1 && chunks > 16 && chunks <= 32 &&
+      !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL) && dreamzs_launch_gauss_smem_bytes(cfg, 8) <= 227 * 1024) {
+    const int tc = (cfg.nchains_local + 6) / 7 <= sm_count() ? 7 : 8;
+    return tc == 7 ? dreamzs_launch_gauss_7(P, stream) : dreamzs_launch_gauss_8(P, stream);
+  }
   const int threads = 128;
   int G = 32, R = 1;
   if (chunks <= 4) G = 4; else if (chunks <= 8) G = 8; else if (chunks <= 16) G = 16;

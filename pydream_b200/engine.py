@@ -80,7 +80,8 @@ class DreamEngine:
     def __init__(self, ndim, nchains, history, starts, target, prior_kind=None, prior_a=None, prior_b=None, seed=0,
                  nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
                  history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
-                 cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True):
+                 cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True,
+                 generic_kernel=False):
         if not torch.cuda.is_available():
             raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _cabi.load()
@@ -133,7 +134,7 @@ class DreamEngine:
         self.cfg = _cabi.Config(abi_version=_cabi.ABI_VERSION, ndim=d, ld=self.ld, nchains_global=N, chain_begin=self.c0,
                                 nchains_local=self.Nl, nCR=nCR, ngamma=gamma_levels, nDEpairs=DEpairs, multitry=multitry,
                                 hardboundaries=int(bool(hardboundaries)), history_thin=self.thin,
-                                target_kind=int(target.kind), flags=_cabi.FLAG_ALL_FLAT if self.all_flat else 0,
+                                target_kind=int(target.kind), flags=(_cabi.FLAG_ALL_FLAT if self.all_flat else 0) | (_cabi.FLAG_GENERIC_KERNEL if generic_kernel else 0),
                                 snooker=snooker, p_gamma_unity=p_gamma_unity, lamb=lamb, zeta=zeta, seed=int(seed) & (2 ** 64 - 1))
         ws = self.lib.dreamzs_adapt_workspace_bytes(C.byref(self.cfg))
         self.workspace = torch.zeros(max(int(ws), 8) // 8 + 1, **f64)

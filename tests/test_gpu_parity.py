@@ -122,3 +122,19 @@ def test_fused_window_equals_single_steps():
     parts = [_run(eng, 1) for _ in range(meta['T'])]
     for i in range(3):
         np.testing.assert_array_equal(a[i], np.concatenate([p[i] for p in parts], axis=0))
+
+
+def test_gauss_kernel_equals_generic_kernel():
+    """The CTA-synchronous dense-Gaussian kernel (TMA-staged rows, shared quadratic forms) and the generic
+    lane-group kernel consume the same random streams: identical decisions, logp within tolerance."""
+    from pydream_b200.engine import DreamEngine
+    rng = np.random.default_rng(77)
+    d, N, T = 100, 1031, 43      # N not a multiple of the chains-per-CTA tile
+    tgt = make_target(dict(kind='gaussian', d=d))
+    hist = rng.uniform(-5, 15, size=(2 * N + 5, d))
+    kw = dict(seed=9, snooker=.15, history_thin=7, DEpairs=2)
+    a = _run(DreamEngine(d, N, hist, hist[:N], tgt, **kw), T)
+    b = _run(DreamEngine(d, N, hist, hist[:N], tgt, generic_kernel=True, **kw), T)
+    np.testing.assert_array_equal(a[2], b[2])
+    assert np.all(np.abs(a[1] - b[1]) <= logp_tol(b[1]))
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-10, atol=1e-11)

@@ -1,0 +1,115 @@
+"""run_dream drop-in behaviour on the GPU, mirroring the reference's own integration tests
+(pydream/tests/test_dream.py:397-497, 629-705): return shapes, archive file layout and length,
+archive tail == multiset of returned samples at history_thin=1, restart files, hard boundaries."""
+import os
+
+import numpy as np
+import pytest
+from scipy.stats import norm, uniform
+
+from pydream_b200 import targets
+from pydream_b200.core import run_dream
+from pydream_b200.convergence import Gelman_Rubin
+from pydream_b200.parameters import SampledParam, FlatParam
+
+pytestmark = pytest.mark.gpu
+
+
+def multidmodel():
+    mu = np.array([-6.6, 3, 1.0, -.12])
+    sd = np.array([.13, 5, .9, 1.0])
+    return [SampledParam(norm, loc=mu, scale=sd)], targets.SumShift(4, 3.0)
+
+
+def multidmodel_uniform():
+    lower = np.array([-5, -9, 5, 3])
+    upper = np.array([10, 2, 7, 8])
+    return [SampledParam(uniform, loc=lower, scale=upper - lower)], targets.SumShift(4, 3.0)
+
+
+def test_return_shapes_and_history_file(tmp_path, monkeypatch):
+    """test_history_correct_after_sampling_simple_model (test_dream.py:629-646) + length formula (:648-668)."""
+    monkeypatch.chdir(tmp_path)
+    params, like = multidmodel()
+    nchains, niter = 5, 20
+    sampled, logps = run_dream(params, like, niterations=niter, nchains=nchains, multitry=False, parallel=False,
+                               history_thin=1, model_name='test_history_correct', adapt_crossover=False, verbose=False, seed=3)
+    assert len(sampled) == nchains and sampled[0].shape == (niter, 4) and logps[0].shape == (niter, 1)
+    history = np.load('test_history_correct_DREAM_chain_history.npy')
+    nseed = 40
+    assert history.ndim == 1 and len(history) == 4 * (nchains * niter + nseed)     # flat float64, rows of ndim
+    tail = history[nseed * 4:].reshape(-1, 4)
+    samples = np.concatenate(sampled)
+    key = lambda a: a[np.lexsort(a.T[::-1])]
+    np.testing.assert_array_equal(key(tail), key(samples))
+    assert os.path.exists('test_history_correct_DREAM_chain_adapted_crossoverprob.npy')
+    assert os.path.exists('test_history_correct_DREAM_chain_adapted_gammalevelprob.npy')
+    # log_ps are log_like + log_prior of the returned points (core.py:115)
+    x = sampled[2][-1]
+    ref = norm(loc=[-6.6, 3, 1.0, -.12], scale=[.13, 5, .9, 1.0]).logpdf(x).sum() + np.sum(x + 3)
+    assert abs(logps[2][-1, 0] - ref) <= 1e-12 * max(1, abs(ref))
+
+
+def test_history_length_with_thinning(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    params, like = multidmodel()
+    run_dream(params, like, niterations=30, nchains=3, history_thin=10, model_name='thin', verbose=False, seed=1)
+    history = np.load('thin_DREAM_chain_history.npy')
+    assert len(history) == 4 * ((3 * 30) // 10 + 40)
+
+
+def test_restart_uses_saved_files(tmp_path, monkeypatch):
+    """restart=True reloads <model_name>_DREAM_chain_history.npy and the adapted probabilities
+    (core.py:46-62, 255-263)."""
+    monkeypatch.chdir(tmp_path)
+    params, like = multidmodel()
+    s1, _ = run_dream(params, like, niterations=40, nchains=3, history_thin=2, model_name='rs', verbose=False, seed=5)
+    h1 = np.load('rs_DREAM_chain_history.npy')
+    cr1 = np.load('rs_DREAM_chain_adapted_crossoverprob.npy')
+    assert abs(cr1.sum() - 1) < 1e-12
+    starts = [s1[c][-1] for c in range(3)]
+    s2, _ = run_dream(params, like, niterations=20, nchains=3, history_thin=2, model_name='rs', verbose=False,
+                      restart=True, start=starts, seed=6)
+    h2 = np.load('rs_DREAM_chain_history.npy')
+    assert len(h2) == len(h1) + 4 * (3 * 20 // 2)
+    np.testing.assert_array_equal(h2[:len(h1)], h1)
+    assert s2[0].shape == (20, 4)
+
+
+def test_boundaries_obeyed_aftersampling():
+    """test_dream.py:670-705: uniform priors + hardboundaries -> no sample outside the box."""
+    params, like = multidmodel_uniform()
+    sampled, logps = run_dream(params, like, niterations=1000, nchains=5, verbose=False, save_history=False, seed=2)
+    lower, upper = np.array([-5, -9, 5, 3]), np.array([10, 2, 7, 8])
+    for ch in sampled:
+        assert np.all(ch >= lower) and np.all(ch <= upper)
+    assert np.all(np.isfinite(np.concatenate(logps)))
+
+
+def test_start_handling_and_flat_prior():
+    """FlatParam needs history_file + start + start_random=False (both analytic examples do this,
+    dream_ex_ndim_gaussian.py:65); a single start array is broadcast to every chain (core.py:77-78)."""
+    d = 10
+    rng = np.random.default_rng(0)
+    hist = rng.normal(size=(100, d))
+    like = targets.BimodalMixture.benchmark(d)
+    params = FlatParam(test_value=np.zeros(d))
+    sampled, logps = run_dream(params, like, niterations=50, nchains=3, start=[hist[c] for c in range(3)],
+                               start_random=False, history_file=hist, multitry=5, verbose=False, save_history=False, seed=8)
+    assert len(sampled) == 3 and sampled[0].shape == (50, d)
+    s2, _ = run_dream(params, like, niterations=5, nchains=3, start=hist[0], start_random=False, history_file=hist,
+                      verbose=False, save_history=False, seed=8)
+    assert s2[1].shape == (5, d)
+    rhat = Gelman_Rubin(sampled)
+    assert rhat.shape == (d,) and np.all(np.isfinite(rhat))
+
+
+def test_converges_to_gaussian_target():
+    """Distributional sanity on the 10-D standard-normal prior with a flat likelihood (BASELINE config 1)."""
+    d = 10
+    params = [SampledParam(norm, loc=np.zeros(d), scale=np.ones(d))]
+    sampled, _ = run_dream(params, targets.Constant(d, 0.0), niterations=3000, nchains=64, verbose=False,
+                           save_history=False, seed=11)
+    x = np.concatenate([s[1500:] for s in sampled])
+    assert np.all(np.abs(x.mean(axis=0)) < 0.1) and np.all(np.abs(x.std(axis=0) - 1) < 0.1)
+    assert np.all(Gelman_Rubin(sampled) < 1.1)

@@ -1,0 +1,57 @@
+"""Minimal driver for ncu: runs a few fused-step launches of the C2 workload (no CPU arm, no e2e, no
+subprocesses).  usage: python tools/profile_step.py [--generic] [--iters 40] [--chains 1024] [--dim 100]"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--generic', action='store_true')
+    ap.add_argument('--iters', type=int, default=41)
+    ap.add_argument('--chains', type=int, default=1024)
+    ap.add_argument('--dim', type=int, default=100)
+    ap.add_argument('--nseed', type=int, default=262144)
+    ap.add_argument('--snooker', type=float, default=.1)
+    ap.add_argument('--target', default='gaussian')
+    ap.add_argument('--multitry', type=int, default=1)
+    ap.add_argument('--time', action='store_true', help='print CUDA-event timing of the run')
+    a = ap.parse_args()
+    import torch
+    from pydream_b200 import targets
+    from pydream_b200.engine import DreamEngine
+    rng = np.random.default_rng(1)
+    d, N = a.dim, a.chains
+    if a.target == 'gaussian':
+        tgt = targets.CorrelatedGaussian.benchmark(d)
+        hist = rng.uniform(-5, 15, size=(a.nseed, d))
+    elif a.target == 'mixture':
+        tgt = targets.BimodalMixture.benchmark(d)
+        hist = rng.normal(size=(a.nseed, d))
+    else:
+        tgt = targets.Banana(d)
+        hist = rng.normal(size=(a.nseed, d))
+    eng = DreamEngine(d, N, hist, hist[:N], tgt, seed=0, snooker=a.snooker, history_thin=10, multitry=a.multitry,
+                      record_decisions=False, generic_kernel=a.generic)
+    eng.run(11)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launches
+    e0.record()
+    eng.run(a.iters)
+    e1.record()
+    torch.cuda.synchronize()
+    if a.time:
+        ms = e0.elapsed_time(e1)
+        print('%s d=%d N=%d: %d iterations in %.3f ms -> %.2f us/iter, %.1f M chain-steps/s, %d launches'
+              % ('generic' if a.generic else 'auto', d, N, a.iters, ms, 1e3 * ms / a.iters, N * a.iters / ms / 1e3,
+                 eng.launches - l0))
+
+
+if __name__ == '__main__':
+    main()
