@@ -109,7 +109,7 @@ def test_converges_to_gaussian_target():
     d = 10
     params = [SampledParam(norm, loc=np.zeros(d), scale=np.ones(d))]
     sampled, _ = run_dream(params, targets.Constant(d, 0.0), niterations=3000, nchains=64, verbose=False,
-                           save_history=False, seed=11)
+                           save_history=False, seed=11, nseedchains=256)
     x = np.concatenate([s[1500:] for s in sampled])
     assert np.all(np.abs(x.mean(axis=0)) < 0.1) and np.all(np.abs(x.std(axis=0) - 1) < 0.1)
     assert np.all(Gelman_Rubin(sampled) < 1.1)
