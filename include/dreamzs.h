@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DREAMZS_ABI_VERSION 1
+#define DREAMZS_ABI_VERSION 2
 
 /* status codes */
 #define DREAMZS_OK 0
@@ -44,10 +44,12 @@ extern "C" {
 #define DREAMZS_MAX_DEPAIRS 8
 #define DREAMZS_MAX_MULTITRY 16
 #define DREAMZS_MAX_NDIM 1024
+#define DREAMZS_GAUSS_REFRESH_WINDOWS 4
 
 /* dreamzs_config.flags */
 #define DREAMZS_FLAG_ALL_FLAT 1  /* every prior is FLAT: the kernels skip prior evaluation and bounds */
 #define DREAMZS_FLAG_GENERIC_KERNEL 2 /* always use the generic lane-group kernel (A/B testing of the specialised ones) */
+#define DREAMZS_FLAG_NO_WINDOW_KERNEL 4 /* do not use the dense-Gaussian window kernel (A/B testing) */
 
 /* analytic log-likelihoods evaluated in-register (pydream_b200/targets.py) */
 enum dreamzs_target_kind {
@@ -106,6 +108,13 @@ typedef struct dreamzs_state {
   const double *prior_b;     /* ndim */
   const double *mins;        /* ndim (Dream.mins, Dream.py:86-105) */
   const double *maxs;        /* ndim */
+  /* Optional (may be NULL): carried state of the dense-Gaussian window kernel, maintained by
+   * dreamzs_init_logp / dreamzs_step: gauss_Y[c] = invC x_c (nchains_local x ld), gauss_Q[c] = x_c . invC x_c.
+   * When both are given (flat priors, one DE pair, no multi-try, 64 < ld <= 128) the quadratic form of a
+   * proposal is updated incrementally, Q(x+dx) = Q + 2 dx.y + dx.(invC dx), and re-derived from x every
+   * DREAMZS_GAUSS_REFRESH_WINDOWS windows of history_thin iterations. */
+  double *gauss_Y;
+  double *gauss_Q;
 } dreamzs_state;
 
 /* Per-launch outputs (device pointers; any may be NULL except trace/trace_logp). */

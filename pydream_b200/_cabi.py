@@ -10,11 +10,12 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libdreamzs.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, E_BADARG, E_LAUNCH, E_UNSUPPORTED = 0, -1, -2, -3
 MAX_NCR, MAX_NGAMMA, MAX_DEPAIRS, MAX_MULTITRY, MAX_NDIM = 16, 8, 8, 16, 1024
 FLAG_ALL_FLAT = 1
 FLAG_GENERIC_KERNEL = 2
+FLAG_NO_WINDOW_KERNEL = 4
 PRIOR_FLAT, PRIOR_NORMAL, PRIOR_UNIFORM = 0, 1, 2
 
 EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_adapt_workspace_bytes',
@@ -34,7 +35,8 @@ class State(C.Structure):
     _fields_ = [('Z', C.c_void_p), ('Z_capacity_rows', C.c_int64), ('X', C.c_void_p), ('last_prior', C.c_void_p),
                 ('last_like', C.c_void_p), ('cr_probs', C.c_void_p), ('gamma_probs', C.c_void_p),
                 ('gamma_table', C.c_void_p), ('target_table', C.c_void_p), ('prior_kind', C.c_void_p),
-                ('prior_a', C.c_void_p), ('prior_b', C.c_void_p), ('mins', C.c_void_p), ('maxs', C.c_void_p)]
+                ('prior_a', C.c_void_p), ('prior_b', C.c_void_p), ('mins', C.c_void_p), ('maxs', C.c_void_p),
+                ('gauss_Y', C.c_void_p), ('gauss_Q', C.c_void_p)]
 
 
 class Trace(C.Structure):

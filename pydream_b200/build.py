@@ -18,6 +18,7 @@ LIB = os.path.join(HERE, 'libdreamzs.so')
 
 STEP_VARIANTS = [(4, 1), (8, 1), (16, 1), (32, 1), (32, 2), (32, 4), (32, 8)]
 GAUSS_VARIANTS = [7, 8]
+GWIN_VARIANTS = [7, 8]
 PLAIN_UNITS = ['dreamzs_cabi.cu', 'dreamzs_adapt.cu', 'dreamzs_gr.cu']
 
 # -fmad=false: parity-sensitive element-wise arithmetic must round like numpy;
@@ -59,6 +60,9 @@ def build(force=False, verbose=False):
                      ['-DDZ_G=%d' % g, '-DDZ_R=%d' % r], hdr_mtime, force))
     for tc in GAUSS_VARIANTS:
         jobs.append((os.path.join(CSRC, 'dreamzs_gauss_inst.cu'), os.path.join(OBJ, 'gauss_%d.o' % tc),
+                     ['-DDZ_TC=%d' % tc], hdr_mtime, force))
+    for tc in GWIN_VARIANTS:
+        jobs.append((os.path.join(CSRC, 'dreamzs_gwin_inst.cu'), os.path.join(OBJ, 'gwin_%d.o' % tc),
                      ['-DDZ_TC=%d' % tc], hdr_mtime, force))
     for u in PLAIN_UNITS:
         jobs.append((os.path.join(CSRC, u), os.path.join(OBJ, u.replace('.cu', '.o')), [], hdr_mtime, force))

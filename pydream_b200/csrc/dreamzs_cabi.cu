@@ -10,6 +10,14 @@ DZ_DECL(4, 1) DZ_DECL(8, 1) DZ_DECL(16, 1) DZ_DECL(32, 1) DZ_DECL(32, 2) DZ_DECL
 int dreamzs_launch_gauss_7(const dreamzs::StepParams &, cudaStream_t);
 int dreamzs_launch_gauss_8(const dreamzs::StepParams &, cudaStream_t);
 size_t dreamzs_launch_gauss_smem_bytes(const dreamzs_config &cfg, int TC);
+int dreamzs_launch_gwin_7(dreamzs::StepParams &, cudaStream_t);
+int dreamzs_launch_gwin_8(dreamzs::StepParams &, cudaStream_t);
+int dreamzs_gwin_usable(const dreamzs_config &cfg, int TC);
+int dreamzs_launch_gauss_refresh(const dreamzs::StepParams &, cudaStream_t);
+
+static long long *g_phase_buffer = nullptr;
+// profiling aid (not part of include/dreamzs.h): CTA 0 of the window kernel writes clock64() stamps of its phases
+extern "C" void dreamzs_debug_set_phase_buffer(void *device_ptr) { g_phase_buffer = (long long *)device_ptr; }
 
 static int sm_count() {
   static int n = 0;
@@ -46,12 +54,29 @@ static int check_cfg(const dreamzs_config *cfg, const dreamzs_state *st) {
   return DREAMZS_OK;
 }
 
+static bool gwin_eligible(const StepParams &P) {
+  const dreamzs_config &cfg = P.cfg;
+  const int chunks = cfg.ld / 4;
+  return cfg.target_kind == DREAMZS_TARGET_GAUSSIAN_DENSE && cfg.multitry == 1 && cfg.nDEpairs == 1 && P.all_flat &&
+         chunks > 16 && chunks <= 32 && P.st.gauss_Y && P.st.gauss_Q && !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL) &&
+         !(cfg.flags & DREAMZS_FLAG_NO_WINDOW_KERNEL) && dreamzs_gwin_usable(cfg, 8);
+}
+
 static int dispatch(StepParams &P, cudaStream_t stream) {
   const dreamzs_config &cfg = P.cfg;
   const int chunks = cfg.ld / 4;
   P.table_doubles = table_doubles_of(&cfg);
   if (P.table_doubles < 0) return DREAMZS_E_UNSUPPORTED;
   P.nslots = cfg.multitry == 1 ? 1 : cfg.multitry + 1;
+  // dense Gaussian, flat priors, one DE pair, no multi-try, carried y = invC x: window kernel (dreamzs_gwin_kernel.cuh)
+  if (gwin_eligible(P)) {
+    if (P.init_only) return DREAMZS_OK;   // handled by the caller (generic evaluation + dreamzs_launch_gauss_refresh)
+    const int64_t t = P.iter_begin, thin = cfg.history_thin;
+    P.gw_refresh = (t == 0 || ((t - 1) % thin == 0 && ((t - 1) / thin) % DREAMZS_GAUSS_REFRESH_WINDOWS == 0)) ? 1 : 0;
+    P.dbg = g_phase_buffer;
+    const int tc = (cfg.nchains_local + 6) / 7 <= sm_count() ? 7 : 8;
+    return tc == 7 ? dreamzs_launch_gwin_7(P, stream) : dreamzs_launch_gwin_8(P, stream);
+  }
   // dense Gaussian, no multi-try, one warp-wide chunk row: CTA-synchronous kernel (dreamzs_gauss_kernel.cuh)
   if (!P.init_only && cfg.target_kind == DREAMZS_TARGET_GAUSSIAN_DENSE && cfg.multitry == 1 && chunks > 16 && chunks <= 32 &&
       !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL) && dreamzs_launch_gauss_smem_bytes(cfg, 8) <= 227 * 1024) {
@@ -84,6 +109,13 @@ extern "C" int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state 
   if (cfg->nchains_local == 0) return DREAMZS_OK;
   StepParams P{};
   P.cfg = *cfg; P.st = *st; P.init_only = 1; P.all_flat = all_flat_hint(cfg);
+  if (gwin_eligible(P)) {
+    StepParams G = P;
+    G.st.gauss_Y = nullptr;   // evaluate last_prior / last_like with the generic path ...
+    rc = dispatch(G, (cudaStream_t)stream);
+    if (rc != DREAMZS_OK) return rc;
+    return dreamzs_launch_gauss_refresh(P, (cudaStream_t)stream);   // ... and derive y = invC x, Q = x.y
+  }
   return dispatch(P, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,584 @@
+// Window kernel for the dense-Gaussian target (BASELINE config C2), sm_100a.
+//
+// The CTA-synchronous kernel (dreamzs_gauss_kernel.cuh) keeps the whole of Dream.astep on the
+// critical path of every iteration: ~17 k cycles per iteration of which ~1.1 k are the quadratic
+// forms.  This kernel takes everything that does not depend on the chain state off that path.
+//
+// For a flat prior and one DE pair the jump of iteration t,  dx = (e*gamma)*(z_r1 - z_r2) + zeta
+// with its crossover mask, the snooker rows, the accept uniform -- everything except the current
+// state x -- is a function of the Philox counters and of the archive, which is constant inside a
+// launch.  And with y = invC x and Q = x.y carried per chain, the quadratic form of a proposal is
+//     Q(x + dx) = Q + 2 dx.y + dx.(invC dx),
+// where w = invC dx does not depend on x either.  So a launch works in batches of NB iterations
+// of the CTA's TC chains (NB*TC "columns"):
+//   G  (warp per column)  all draws of the column in one lane-parallel Philox pass; archive rows
+//                         TMA-staged straight into the shared-memory slots that will hold the
+//                         jump (UBLKCP + mbarrier complete_tx); dx, zeta and the crossover mask
+//   M  (warp per tile)    W = invC * [dx columns | snooker z columns | x columns on refresh]:
+//                         register-tiled fp64 products, 4 rows x TC columns per thread, K split
+//                         3-fold over warps, one (column group, K range) per warp
+//   C  (warp per chain)   the Markov chain itself: per iteration 2 adds, one 4-wide dot product and
+//                         ONE warp reduction, the Metropolis test, trace write, archive append
+// The snooker move is linear in the state as well: dx = c (x - z), invC dx = c (y - invC z), so
+// its column of M is invC z.  y and Q are refreshed from x every DREAMZS_GAUSS_REFRESH_WINDOWS
+// windows so rounding drift stays orders of magnitude below the 1e-12 parity tolerance.
+//
+// RNG consumption, decisions and element-wise arithmetic are those of dreamzs_step_kernel / the
+// oracle; only the summation order of the quadratic form differs.
+#pragma once
+#include "dreamzs_gauss_kernel.cuh"
+
+namespace dreamzs {
+
+constexpr int GW_THREADS = 512;
+constexpr int GW_WARPS = GW_THREADS / 32;
+constexpr int GW_KS = 3;       // K split of the products; fixed: the summation order is part of the result
+constexpr int GW_MAXNB = 5;    // iterations per batch: GW_MAXNB * GW_KS tiles <= GW_WARPS
+constexpr int GW_MAXCOLW = 3;  // columns a warp generates per batch: ceil(GW_MAXNB * 8 / GW_WARPS)
+
+struct GwinLayout {
+  int d2, ncol;
+  size_t oAt, oWc, oJc, oZc, oXs, oYs, oGam, oSdot, oLogu, oGsn, oProbs, oMbar, oMeta, bytes;
+};
+
+__host__ __device__ inline GwinLayout gwin_layout(int d, int ld, int TC, int NB, int ngamma) {
+  GwinLayout L;
+  L.d2 = (d + 1) & ~1;
+  L.ncol = NB * TC;
+  size_t o = 0;
+  L.oAt = o;    o += (size_t)L.d2 * ld;              // precision matrix, transposed, row stride ld
+  L.oWc = o;    o += (size_t)(L.ncol + TC) * ld;     // dx / z columns -> invC * column; + TC refresh columns
+  L.oJc = o;    o += (size_t)L.ncol * ld;            // (e*gamma)*diff      | snooker: z
+  L.oZc = o;    o += (size_t)L.ncol * ld;            // zeta                | snooker: z1 - z2
+  L.oXs = o;    o += (size_t)TC * ld;                // chain states between the C phases
+  L.oYs = o;    o += (size_t)TC * ld;
+  L.oGam = o;   o += ((size_t)ngamma * d + 1) & ~(size_t)1;
+  L.oSdot = o;  o += L.ncol;
+  L.oLogu = o;  o += L.ncol;
+  L.oGsn = o;   o += L.ncol;
+  L.oProbs = o; o += 32 + 4 * TC;
+  L.oMbar = o;  o += L.ncol + 1;
+  L.oMeta = o;  o += (L.ncol + 1) / 2;
+  L.bytes = o * sizeof(double);
+  return L;
+}
+
+template <int TC>
+__global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepParams P) {
+  extern __shared__ __align__(16) double smem[];
+  const int d = P.cfg.ndim, ld = P.cfg.ld, NB = P.gw_nb;
+  const GwinLayout L = gwin_layout(d, ld, TC, NB, P.cfg.ngamma);
+  const int d2 = L.d2, ncol = L.ncol;
+  double *At = smem + L.oAt, *Wc = smem + L.oWc, *Jc = smem + L.oJc, *Zc = smem + L.oZc;
+  double *Xs = smem + L.oXs, *Ys = smem + L.oYs, *gam = smem + L.oGam;
+  double *sdot = smem + L.oSdot, *logu = smem + L.oLogu, *gsn = smem + L.oGsn;
+  double *probs = smem + L.oProbs, *cst = probs + 32;   // cst: per chain [Q, last_prior, last_like, -]
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L.oMbar);   // [ncol] columns, [ncol] precision matrix
+  uint32_t *meta = reinterpret_cast<uint32_t *>(smem + L.oMeta);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double logF = P.st.target_table[0];
+  int dbg_n = 0;
+#define GW_STAMP() do { if (P.dbg && blockIdx.x == 0 && tid == 0) P.dbg[dbg_n] = clock64(); ++dbg_n; } while (0)
+  GW_STAMP();   // 0: kernel entry
+
+  const int i0 = 4 * lane;
+  const bool own = i0 < ld;          // lane owns a 4-dimension chunk of a row
+  const int64_t M = P.archive_rows;
+  const uint32_t row_bytes = (uint32_t)ld * 8u;
+  const uint32_t s0 = P.cfg.snooker != 0 ? 1u : 0u;   // multinomial call number of the CR draw
+  const uint32_t k0 = (uint32_t)P.cfg.seed, k1 = (uint32_t)(P.cfg.seed >> 32);
+  const int cta_chain0 = blockIdx.x * TC;
+  const int nch = min(TC, P.cfg.nchains_local - cta_chain0);   // chains of this CTA
+
+  // ---- prologue: one TMA bulk copy brings the precision matrix; chain states -> shared memory
+  if (tid < ncol + 1) mbar_init(mbar + tid, 1);
+  if (tid < 32) {
+    double v = 0.0;
+    if (tid < 16) v = tid < P.cfg.nCR ? P.st.cr_probs[tid] : 0.0;
+    else if (tid < 24) v = tid - 16 < P.cfg.ngamma ? P.st.gamma_probs[tid - 16] : 0.0;
+    else if (tid == 24) v = P.cfg.snooker;
+    else if (tid == 26) v = P.cfg.p_gamma_unity;
+    probs[tid] = v;
+  }
+  for (int i = tid; i < P.cfg.ngamma * d; i += GW_THREADS) {   // gamma_table[level][0][:] (one DE pair)
+    const int lv = i / d;
+    gam[i] = P.st.gamma_table[(size_t)lv * P.cfg.nDEpairs * d + (i - lv * d)];
+  }
+  if ((d & 1) && tid < ld) At[(size_t)d * ld + tid] = 0.0;     // padding row of the j-pair loop
+  if (warp < nch) {
+    const int c_local = cta_chain0 + warp;
+    if (own) {
+      const double *xrow = P.st.X + (size_t)c_local * ld + i0;
+      *reinterpret_cast<double2 *>(Xs + warp * ld + i0) = *reinterpret_cast<const double2 *>(xrow);
+      *reinterpret_cast<double2 *>(Xs + warp * ld + i0 + 2) = *reinterpret_cast<const double2 *>(xrow + 2);
+      if (!P.gw_refresh) {
+        const double *yrow = P.st.gauss_Y + (size_t)c_local * ld + i0;
+        *reinterpret_cast<double2 *>(Ys + warp * ld + i0) = *reinterpret_cast<const double2 *>(yrow);
+        *reinterpret_cast<double2 *>(Ys + warp * ld + i0 + 2) = *reinterpret_cast<const double2 *>(yrow + 2);
+      }
+    }
+    if (lane == 0) {
+      cst[warp * 4 + 0] = P.gw_refresh ? 0.0 : P.st.gauss_Q[c_local];
+      cst[warp * 4 + 1] = P.st.last_prior[c_local];
+      cst[warp * 4 + 2] = P.st.last_like[c_local];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    fence_proxy_async();
+    const uint32_t bytes = (uint32_t)d * row_bytes;
+    mbar_expect_tx(mbar + ncol, bytes);
+    tma_load_row(At, P.st.target_table + 2, bytes, mbar + ncol);
+  }
+  GW_STAMP();   // 1: prologue done
+
+  const int nq = ld / 4;                                   // row groups of a tile = lanes of a tile warp
+  const int jl = ((d2 / 2 + GW_KS - 1) / GW_KS) * 2;       // K range of a split (even)
+
+  int done = 0;
+  for (int batch = 0; done < P.niter; ++batch) {
+    const int nb = min(NB, P.niter - done);
+    const int nbc = nb * TC;                               // columns of this batch: col = iteration * TC + chain
+    const bool do_refresh = P.gw_refresh && batch == 0;
+    const uint32_t parity = (uint32_t)(batch & 1);
+    // ================================================================ G: generation (warp per column)
+    {
+      // ---- S: scalar draws and archive rows of the warp's columns, one Philox block per lane:
+      //      lanes 0-5: snooker, CR, gamma level, gamma unity (Dream.py:542-599, 615), first two
+      //      np.random.uniform() (snooker gamma :618 / Metropolis :993); lanes 8-10: random.sample calls 0-2
+      int c_snk[GW_MAXCOLW], c_cr[GW_MAXCOLW], c_lvl[GW_MAXCOLW], c_unity[GW_MAXCOLW];
+      double c_lu[GW_MAXCOLW], c_u0[GW_MAXCOLW];
+#pragma unroll
+      for (int k = 0; k < GW_MAXCOLW; ++k) {
+        const int col = warp + GW_WARPS * k;
+        c_snk[k] = c_cr[k] = c_lvl[k] = c_unity[k] = 0; c_lu[k] = c_u0[k] = 0.0;
+        const int itb = col / TC, ch = col - itb * TC;
+        if (col < nbc && ch < nch) {
+          const uint32_t iter = (uint32_t)(P.iter_begin + done + itb);
+          const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
+          uint32_t call = 0, st = ST_MULTINOMIAL;
+          const double *pp = probs + 24;
+          int n = 2;
+          if (lane == 1) { call = s0; pp = probs; n = P.cfg.nCR; }
+          else if (lane == 2) { call = s0 + 1; pp = probs + 16; n = P.cfg.ngamma; }
+          else if (lane == 3) { call = s0 + 2; pp = probs + 26; }
+          else if (lane == 4) { st = ST_UNIFORM_SCAL; }
+          else if (lane == 5) { call = 1; st = ST_UNIFORM_SCAL; }
+          else if (lane >= 8) { call = (uint32_t)(lane - 8) & 3u; st = ST_SAMPLE; }
+          const uint4 w = philox4x32(0u, (call << 3) | st, iter, c_global, k0, k1);
+          const double u = u53_of(w.x, w.y);
+          double acc = 0.0;
+          int idx = n - 1;
+          bool found = false;
+          for (int j = 0; j < n; ++j) {
+            acc = acc + pp[j];
+            if (!found && u < acc) { idx = j; found = true; }
+          }
+          const double lg = log(u);
+          if (k == 0) GW_STAMP();   // s1: philox, multinomial, log
+          const int snk = (s0 != 0u) && __shfl_sync(0xffffffffu, idx, 0) == 0;
+          c_snk[k] = snk;
+          c_cr[k] = __shfl_sync(0xffffffffu, idx, 1);
+          c_lvl[k] = __shfl_sync(0xffffffffu, idx, 2);
+          c_unity[k] = __shfl_sync(0xffffffffu, idx, 3);
+          c_u0[k] = __shfl_sync(0xffffffffu, u, 4);
+          const double lu0 = __shfl_sync(0xffffffffu, lg, 4), lu1 = __shfl_sync(0xffffffffu, lg, 5);
+          c_lu[k] = snk ? lu1 : lu0;
+          if (k == 0) GW_STAMP();   // s2: shuffles
+          // archive rows (sample_from_history, Dream.py:646-668), TMA-staged into the column's slots:
+          //   DE      z_r1 -> J slot, z_r2 -> zeta slot;   snooker  z -> J slot, z1 -> W slot, z2 -> zeta slot
+          int64_t r0 = (int64_t)(((uint64_t)w.x * (uint64_t)M) >> 32);
+          int64_t r1 = (int64_t)(((uint64_t)w.y * (uint64_t)(M - 1)) >> 32);
+          if (r1 >= r0) r1 += 1;
+          if (lane == 8) {
+            fence_proxy_async();   // earlier generic-proxy accesses of the slots are ordered before the async writes
+            mbar_expect_tx(mbar + col, row_bytes * (snk ? 3u : 2u));
+          }
+          __syncwarp();
+          if (k == 0) GW_STAMP();   // s3: fence + expect_tx
+          double *js = Jc + (size_t)col * ld, *zs = Zc + (size_t)col * ld, *ws = Wc + (size_t)col * ld;
+          if (!snk) {
+            if (lane == 8) {
+              tma_load_row(js, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
+              tma_load_row(zs, P.st.Z + (size_t)r1 * ld, row_bytes, mbar + col);
+            }
+          } else if (lane >= 8 && lane <= 10) {
+            fence_proxy_async();
+            tma_load_row(lane == 8 ? js : lane == 9 ? ws : zs, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
+          }
+          __syncwarp();
+          if (k == 0) GW_STAMP();   // s4: TMA issued
+        }
+      }
+      GW_STAMP();   // +0: rows requested (warp 0)
+      // ---- V: the columns (generate_proposal_points DE branch, Dream.py:688-726; snooker rows, :808-810)
+#pragma unroll
+      for (int k = 0; k < GW_MAXCOLW; ++k) {
+        const int col = warp + GW_WARPS * k;
+        const int itb = col / TC, ch = col - itb * TC;
+        if (col < nbc && ch < nch) {
+          const uint32_t iter = (uint32_t)(P.iter_begin + done + itb);
+          const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
+          const int snk = c_snk[k], cr_idx = c_cr[k], lvl_idx = c_lvl[k];
+          double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
+          if (!snk) {
+            double zeta[4] = {0, 0, 0, 0}, e[4] = {1, 1, 1, 1};
+            unsigned reset = 15u;
+            int dprime = 0;
+            if (own && i0 < d) {
+              double nz[4];
+              normal4(philox4x32((uint32_t)lane, (0u << 3) | ST_NORMAL, iter, c_global, k0, k1), nz);
+              const uint4 we = philox4x32((uint32_t)lane, (0u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
+              const uint4 wu = philox4x32((uint32_t)lane, (1u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
+              const uint32_t wev[4] = {we.x, we.y, we.z, we.w}, wuv[4] = {wu.x, wu.y, wu.z, wu.w};
+              // U = w 2^-32 exactly, so U < CR <=> w < ceil(CR 2^32) and U > CR <=> w > floor(CR 2^32)
+              const double CRs = ((double)(cr_idx + 1) / (double)P.cfg.nCR) * 4294967296.0;
+              const uint64_t t_lt = (uint64_t)ceil(CRs), t_gt = (uint64_t)floor(CRs);
+              reset = 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                zeta[j] = 0.0 + P.cfg.zeta * nz[j];
+                e[j] = (-P.cfg.lamb + (P.cfg.lamb - (-P.cfg.lamb)) * u32_of(wev[j])) + 1;
+                if (i0 + j < d) {
+                  dprime += ((uint64_t)wuv[j] < t_lt);
+                  if ((uint64_t)wuv[j] > t_gt) reset |= 1u << j;
+                } else reset |= 1u << j;
+              }
+            }
+            dprime = __reduce_add_sync(0xffffffffu, dprime);
+            double gamma = 1.0;
+            if (c_unity[k] != 0) gamma = gam[lvl_idx * d + (dprime >= 1 ? dprime - 1 : d - 1)];
+            if (lane == 0) {
+              meta[col] = (uint32_t)cr_idx | ((uint32_t)lvl_idx << 4) | ((gamma == 1.0) ? 512u : 0u);
+              logu[col] = c_lu[k];
+            }
+            mbar_wait(mbar + col, parity);
+            if (own) {
+              const double2 a01 = *reinterpret_cast<const double2 *>(js), a23 = *reinterpret_cast<const double2 *>(js + 2);
+              const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
+              const double diff[4] = {a01.x - b01.x, a01.y - b01.y, a23.x - b23.x, a23.y - b23.y};
+              double J[4], zt[4], dl[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool keep = !((reset >> j) & 1u);
+                J[j] = keep ? (e[j] * gamma) * diff[j] : 0.0;
+                zt[j] = keep ? zeta[j] : 0.0;
+                dl[j] = J[j] + zt[j];
+              }
+              *reinterpret_cast<double2 *>(js) = make_double2(J[0], J[1]); *reinterpret_cast<double2 *>(js + 2) = make_double2(J[2], J[3]);
+              *reinterpret_cast<double2 *>(zs) = make_double2(zt[0], zt[1]); *reinterpret_cast<double2 *>(zs + 2) = make_double2(zt[2], zt[3]);
+              *reinterpret_cast<double2 *>(ws) = make_double2(dl[0], dl[1]); *reinterpret_cast<double2 *>(ws + 2) = make_double2(dl[2], dl[3]);
+            }
+          } else {
+            if (lane == 0) {
+              const double gamma = 1.2 + (2.2 - 1.2) * c_u0[k];
+              meta[col] = 256u | (uint32_t)cr_idx | ((uint32_t)lvl_idx << 4) | ((gamma == 1.0) ? 512u : 0u);
+              gsn[col] = gamma;
+              logu[col] = c_lu[k];
+            }
+            mbar_wait(mbar + col, parity);
+            if (own) {
+              const double2 z01 = *reinterpret_cast<const double2 *>(js), z23 = *reinterpret_cast<const double2 *>(js + 2);
+              const double2 a01 = *reinterpret_cast<const double2 *>(ws), a23 = *reinterpret_cast<const double2 *>(ws + 2);
+              const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
+              *reinterpret_cast<double2 *>(zs) = make_double2(a01.x - b01.x, a01.y - b01.y);
+              *reinterpret_cast<double2 *>(zs + 2) = make_double2(a23.x - b23.x, a23.y - b23.y);
+              *reinterpret_cast<double2 *>(ws) = z01; *reinterpret_cast<double2 *>(ws + 2) = z23;
+            }
+          }
+        } else if (col < nbc && own) {
+          // column of a chain slot past the end of the shard: keep its product finite
+          double *ws = Wc + (size_t)col * ld + i0;
+          *reinterpret_cast<double2 *>(ws) = make_double2(0.0, 0.0); *reinterpret_cast<double2 *>(ws + 2) = make_double2(0.0, 0.0);
+        }
+      }
+      if (do_refresh && warp < TC && own) {   // refresh columns: x (zero for empty chain slots)
+        double *ws = Wc + (size_t)(ncol + warp) * ld + i0;
+        double2 a = make_double2(0.0, 0.0), b = a;
+        if (warp < nch) { a = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0); b = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0 + 2); }
+        *reinterpret_cast<double2 *>(ws) = a; *reinterpret_cast<double2 *>(ws + 2) = b;
+      }
+    }
+    GW_STAMP();   // +1: columns of warp 0 generated
+    if (batch == 0) mbar_wait(mbar + ncol, 0);   // precision matrix has landed
+    __syncthreads();
+    GW_STAMP();   // +2: all warps generated
+    // ================================================================ M: W = invC * columns (warp per tile)
+    // tile = (column group of TC columns, K range); lane = row group: rows 2l, 2l+1, ld/2+2l, ld/2+2l+1
+    for (int pass = 0; pass < (do_refresh ? 2 : 1); ++pass) {
+      const int ncg = pass == 0 ? nb : 1;
+      const bool active = warp < ncg * GW_KS && lane < nq;
+      const int cgi = warp % ncg, ks = warp / ncg;
+      const int colbase = pass == 0 ? cgi * TC : ncol;
+      double acc[4][TC];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int cc = 0; cc < TC; ++cc) acc[r][cc] = 0.0;
+      if (active) {
+        const int jb = min(d2, ks * jl), je = min(d2, jb + jl);
+        const double *ap = At + 2 * lane;
+        const double *xp = Wc + (size_t)colbase * ld;
+        const int hb = ld / 2;
+#pragma unroll 1
+        for (int j = jb; j < je; j += 2) {
+          const double2 a0 = *reinterpret_cast<const double2 *>(ap + (size_t)j * ld);
+          const double2 b0 = *reinterpret_cast<const double2 *>(ap + (size_t)j * ld + hb);
+          const double2 a1 = *reinterpret_cast<const double2 *>(ap + (size_t)(j + 1) * ld);
+          const double2 b1 = *reinterpret_cast<const double2 *>(ap + (size_t)(j + 1) * ld + hb);
+#pragma unroll
+          for (int cc = 0; cc < TC; ++cc) {
+            const double2 x = *reinterpret_cast<const double2 *>(xp + (size_t)cc * ld + j);
+            acc[0][cc] = fma(a0.x, x.x, acc[0][cc]); acc[1][cc] = fma(a0.y, x.x, acc[1][cc]);
+            acc[2][cc] = fma(b0.x, x.x, acc[2][cc]); acc[3][cc] = fma(b0.y, x.x, acc[3][cc]);
+            acc[0][cc] = fma(a1.x, x.y, acc[0][cc]); acc[1][cc] = fma(a1.y, x.y, acc[1][cc]);
+            acc[2][cc] = fma(b1.x, x.y, acc[2][cc]); acc[3][cc] = fma(b1.y, x.y, acc[3][cc]);
+          }
+        }
+      }
+      __syncthreads();   // every column has been read: the products may now overwrite them in place
+      if (pass == 0) GW_STAMP();   // +3: products computed
+#pragma unroll 1
+      for (int r = 0; r < GW_KS; ++r) {
+        if (active && ks == r) {
+          double *wp = Wc + (size_t)colbase * ld + 2 * lane;
+          const int hb = ld / 2;
+          if (r > 0) {
+#pragma unroll
+            for (int cc = 0; cc < TC; ++cc) {
+              const double2 ta = *reinterpret_cast<const double2 *>(wp + (size_t)cc * ld);
+              const double2 tb = *reinterpret_cast<const double2 *>(wp + (size_t)cc * ld + hb);
+              acc[0][cc] = ta.x + acc[0][cc]; acc[1][cc] = ta.y + acc[1][cc];
+              acc[2][cc] = tb.x + acc[2][cc]; acc[3][cc] = tb.y + acc[3][cc];
+            }
+          }
+#pragma unroll
+          for (int cc = 0; cc < TC; ++cc) {
+            *reinterpret_cast<double2 *>(wp + (size_t)cc * ld) = make_double2(acc[0][cc], acc[1][cc]);
+            *reinterpret_cast<double2 *>(wp + (size_t)cc * ld + hb) = make_double2(acc[2][cc], acc[3][cc]);
+          }
+        }
+        __syncthreads();
+      }
+    }
+    GW_STAMP();   // +4: products written
+    // ================================================================ C: the chains (warp per chain)
+    if (warp < nch) {
+      const int c_local = cta_chain0 + warp;
+      const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + c_local);
+      double x0[4] = {0, 0, 0, 0}, y0[4] = {0, 0, 0, 0};
+      double Q0 = cst[warp * 4], last_prior = cst[warp * 4 + 1], last_like = cst[warp * 4 + 2];
+      if (own) {
+        const double2 a = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0), b = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0 + 2);
+        x0[0] = a.x; x0[1] = a.y; x0[2] = b.x; x0[3] = b.y;
+      }
+      if (do_refresh) {
+        const double *ws = Wc + (size_t)(ncol + warp) * ld + i0;
+        double part = 0.0;
+        if (own) {
+          const double2 a = *reinterpret_cast<const double2 *>(ws), b = *reinterpret_cast<const double2 *>(ws + 2);
+          y0[0] = a.x; y0[1] = a.y; y0[2] = b.x; y0[3] = b.y;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) part = fma(x0[j], y0[j], part);
+        }
+        Q0 = gsum<32>(part, 0xffffffffu);
+      } else if (own) {
+        const double2 a = *reinterpret_cast<const double2 *>(Ys + warp * ld + i0), b = *reinterpret_cast<const double2 *>(Ys + warp * ld + i0 + 2);
+        y0[0] = a.x; y0[1] = a.y; y0[2] = b.x; y0[3] = b.y;
+      }
+      // dx.(invC dx) of the columns (state independent; unused for snooker columns)
+      {
+        double sd[GW_MAXNB];
+#pragma unroll
+        for (int itb = 0; itb < GW_MAXNB; ++itb) {
+          double part = 0.0;
+          if (itb < nb && own) {
+            const int col = itb * TC + warp;
+            const double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
+            const double2 j01 = *reinterpret_cast<const double2 *>(js), j23 = *reinterpret_cast<const double2 *>(js + 2);
+            const double2 z01 = *reinterpret_cast<const double2 *>(zs), z23 = *reinterpret_cast<const double2 *>(zs + 2);
+            const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
+            part = fma(j01.x + z01.x, w01.x, part); part = fma(j01.y + z01.y, w01.y, part);
+            part = fma(j23.x + z23.x, w23.x, part); part = fma(j23.y + z23.y, w23.y, part);
+          }
+          sd[itb] = part;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int itb = 0; itb < GW_MAXNB; ++itb) sd[itb] += __shfl_xor_sync(0xffffffffu, sd[itb], o);
+        if (lane == 0) {
+#pragma unroll
+          for (int itb = 0; itb < GW_MAXNB; ++itb) if (itb < nb) sdot[itb * TC + warp] = sd[itb];
+        }
+        __syncwarp();
+      }
+      GW_STAMP();   // c0: state loaded, sdot done
+      double *trow_ptr = P.tr.trace + ((size_t)c_local * P.tr.trace_iters + (P.tr.trace_offset + done)) * ld + i0;
+      double *lrow_ptr = P.tr.trace_logp + (size_t)c_local * P.tr.trace_iters + (P.tr.trace_offset + done);
+      uint32_t *drow_ptr = P.tr.decisions ? P.tr.decisions + (size_t)c_local * P.tr.trace_iters + (P.tr.trace_offset + done) : nullptr;
+#pragma unroll 1
+      for (int itb = 0; itb < nb; ++itb) {
+        const int col = itb * TC + warp;
+        const double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
+        double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0};
+        if (own) {
+          const double2 j01 = *reinterpret_cast<const double2 *>(js), j23 = *reinterpret_cast<const double2 *>(js + 2);
+          const double2 z01 = *reinterpret_cast<const double2 *>(zs), z23 = *reinterpret_cast<const double2 *>(zs + 2);
+          const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
+          a[0] = j01.x; a[1] = j01.y; a[2] = j23.x; a[3] = j23.y;
+          b[0] = z01.x; b[1] = z01.y; b[2] = z23.x; b[3] = z23.y;
+          w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y;
+        }
+        const uint32_t mt = meta[col];
+        const int run_snooker = (mt >> 8) & 1;
+        const double lu = logu[col];
+        const double last_logp = 1.0 * last_like + last_prior;
+        double prop[4], wn[4], mr, Qn;
+        if (!run_snooker) {
+          // prop = q0 + e*gamma*diff + zeta (Dream.py:717); Q(prop) = Q + 2 dx.y + dx.(invC dx)
+          double part = 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            prop[j] = x0[j] + a[j] + b[j];
+            wn[j] = w[j];
+            part = fma(prop[j] - x0[j], y0[j], part);
+          }
+          const double dot = gsum<32>(part, 0xffffffffu);
+          Qn = (Q0 + 2.0 * dot) + sdot[col];
+          const double q_logp = 1.0 * (logF - .5 * Qn) + 0.0;
+          mr = nan_to_num(q_logp) - nan_to_num(last_logp);                               // Dream.py:334
+        } else {
+          // snooker_update, Dream.py:827-835 (single-point form); a = z, b = z1 - z2, w = invC z
+          const double gamma = gsn[col];
+          double v[4], t[4];
+          double D = 0.0, S = 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = (i0 + j < d) ? x0[j] - a[j] : 0.0;
+            D = fma(v[j], v[j], D);
+            t[j] = b[j] * v[j];
+          }
+          D = gsum<32>(D, 0xffffffffu);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) S += (D != 0) ? t[j] / D : 0.0;
+          const double sc = nan_to_num(gsum<32>(S, 0xffffffffu));
+          const double cg = gamma * sc;
+          double nn = 0.0, p1 = 0.0, p2 = 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool okd = i0 + j < d;
+            const double o = okd ? x0[j] + gamma * (sc * v[j]) : 0.0;
+            prop[j] = o;
+            const double ww = okd ? o - a[j] : 0.0;
+            nn = fma(ww, ww, nn);
+            wn[j] = cg * (y0[j] - w[j]);              // invC dx = c (y - invC z)
+            const double dl = o - x0[j];
+            p1 = fma(dl, y0[j], p1);
+            p2 = fma(dl, wn[j], p2);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            nn += __shfl_xor_sync(0xffffffffu, nn, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+            p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+          }
+          const double norm = sqrt(nn);
+          const double snk_logp = (norm != 0 ? log(norm) : 0.0) * (d - 1);
+          const double n0 = sqrt(D);
+          const double cur = (n0 != 0 ? log(n0) : 0.0) * (d - 1);
+          Qn = (Q0 + 2.0 * p1) + p2;
+          const double q_logp = 1.0 * (logF - .5 * Qn) + 0.0;
+          mr = nan_to_num((q_logp + snk_logp) - (last_logp + cur));                      // Dream.py:326-332
+        }
+        bool accepted = false;
+        if (isfinite(mr)) accepted = lu < mr;                                            // metrop_select, Dream.py:980-998
+        int changed = 0;
+        if (accepted) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) changed |= (prop[j] != x0[j]);
+        }
+        changed = __any_sync(0xffffffffu, changed);
+        if (changed) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { x0[j] = prop[j]; y0[j] = y0[j] + wn[j]; }
+          Q0 = Qn;
+          last_prior = 0.0;
+          last_like = logF - .5 * Qn;
+        }
+        if (own) {
+          *reinterpret_cast<double2 *>(trow_ptr) = make_double2(x0[0], x0[1]);
+          *reinterpret_cast<double2 *>(trow_ptr + 2) = make_double2(x0[2], x0[3]);
+          if (P.gw_append && done + itb == P.niter - 1) {   // record_history: the last iteration of the launch
+            double *zr = P.st.Z + (size_t)(M + c_global) * ld + i0;
+            *reinterpret_cast<double2 *>(zr) = make_double2(x0[0], x0[1]);
+            *reinterpret_cast<double2 *>(zr + 2) = make_double2(x0[2], x0[3]);
+          }
+        }
+        if (lane == 0) {
+          *lrow_ptr = last_like + last_prior;
+          if (drow_ptr)
+            *drow_ptr = pack_decision(changed, run_snooker, mt & 15, (mt >> 4) & 15, 1, 0, (mt >> 9) & 1, accepted);
+        }
+        trow_ptr += ld; lrow_ptr += 1; if (drow_ptr) drow_ptr += 1;
+        GW_STAMP();   // c: iteration done
+      }
+      // park the chain state for the next batch / the epilogue
+      if (own) {
+        *reinterpret_cast<double2 *>(Xs + warp * ld + i0) = make_double2(x0[0], x0[1]);
+        *reinterpret_cast<double2 *>(Xs + warp * ld + i0 + 2) = make_double2(x0[2], x0[3]);
+        *reinterpret_cast<double2 *>(Ys + warp * ld + i0) = make_double2(y0[0], y0[1]);
+        *reinterpret_cast<double2 *>(Ys + warp * ld + i0 + 2) = make_double2(y0[2], y0[3]);
+      }
+      if (lane == 0) { cst[warp * 4] = Q0; cst[warp * 4 + 1] = last_prior; cst[warp * 4 + 2] = last_like; }
+    }
+    GW_STAMP();   // +5: chain of warp 0 advanced
+    done += nb;
+    __syncthreads();   // the slots are free for the next batch
+  }
+  GW_STAMP();
+  if (warp < nch) {
+    const int c_local = cta_chain0 + warp;
+    if (own) {
+      double *xrow = P.st.X + (size_t)c_local * ld + i0, *yrow = P.st.gauss_Y + (size_t)c_local * ld + i0;
+      *reinterpret_cast<double2 *>(xrow) = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0);
+      *reinterpret_cast<double2 *>(xrow + 2) = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0 + 2);
+      *reinterpret_cast<double2 *>(yrow) = *reinterpret_cast<const double2 *>(Ys + warp * ld + i0);
+      *reinterpret_cast<double2 *>(yrow + 2) = *reinterpret_cast<const double2 *>(Ys + warp * ld + i0 + 2);
+    }
+    if (lane == 0) {
+      P.st.gauss_Q[c_local] = cst[warp * 4];
+      P.st.last_prior[c_local] = cst[warp * 4 + 1];
+      P.st.last_like[c_local] = cst[warp * 4 + 2];
+    }
+  }
+}
+
+// largest batch (iterations) whose tiles fit the CTA's warps and whose buffers fit shared memory; 0 = kernel not usable
+inline int gwin_pick_nb(const dreamzs_config &cfg, int TC, size_t *smem_bytes) {
+  if (cfg.ld > 128 || (cfg.ld & 3)) return 0;
+  for (int nb = GW_MAXNB; nb >= 1; --nb) {
+    if (nb * GW_KS > GW_WARPS || (nb * TC + GW_WARPS - 1) / GW_WARPS > GW_MAXCOLW) continue;
+    const GwinLayout L = gwin_layout(cfg.ndim, cfg.ld, TC, nb, cfg.ngamma);
+    if (L.bytes <= 227 * 1024) { *smem_bytes = L.bytes; return nb; }
+  }
+  return 0;
+}
+
+template <int TC>
+int launch_gwin(StepParams &P, cudaStream_t stream) {
+  size_t smem = 0;
+  P.gw_nb = gwin_pick_nb(P.cfg, TC, &smem);
+  if (P.gw_nb == 0) return DREAMZS_E_UNSUPPORTED;
+  P.gw_append = (P.iter_begin + P.niter - 1) % P.cfg.history_thin == 0 ? 1 : 0;
+  auto kern = dreamzs_gwin_kernel<TC>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return DREAMZS_E_LAUNCH;
+  }
+  const int grid = (P.cfg.nchains_local + TC - 1) / TC;
+  kern<<<grid, GW_THREADS, smem, stream>>>(P);
+  return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;
+}
+
+}  // namespace dreamzs

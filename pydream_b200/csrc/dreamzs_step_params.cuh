@@ -16,6 +16,10 @@ struct StepParams {
   int32_t table_doubles;  // length of the target table
   int32_t nslots;         // proposal slots per chain in shared memory
   int32_t init_only;      // dreamzs_init_logp: evaluate logp(X) and return
+  int32_t gw_nb;          // window kernel: iterations per batch
+  long long *dbg;         // optional phase-timestamp buffer (dreamzs_debug_set_phase_buffer; profiling aid)
+  int32_t gw_append;      // window kernel: the last iteration of the launch appends to the archive
+  int32_t gw_refresh;     // window kernel: re-derive gauss_Y / gauss_Q from X at the start of the launch
 };
 
 }  // namespace dreamzs

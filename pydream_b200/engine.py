@@ -81,7 +81,7 @@ class DreamEngine:
                  nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
                  history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
                  cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True,
-                 generic_kernel=False):
+                 generic_kernel=False, window_kernel=True):
         if not torch.cuda.is_available():
             raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _cabi.load()
@@ -131,10 +131,15 @@ class DreamEngine:
         self.ngamma_updates, self.delta_m_gamma = torch.zeros(gamma_levels, **f64), torch.zeros(gamma_levels, **f64)
         self.gamma_table = torch.from_numpy(gamma_table(gamma_levels, DEpairs, d)).to(self.device)
         self.target_table = torch.from_numpy(device_target_table(target, self.ld)).to(self.device)
+        # carried y = invC x and Q = x.y of the dense-Gaussian window kernel (include/dreamzs.h dreamzs_state)
+        dense = target.kind == T.TARGET_GAUSSIAN_DENSE
+        self.gauss_Y = torch.zeros((self.Nl, self.ld), **f64) if dense else None
+        self.gauss_Q = torch.zeros(self.Nl, **f64) if dense else None
         self.cfg = _cabi.Config(abi_version=_cabi.ABI_VERSION, ndim=d, ld=self.ld, nchains_global=N, chain_begin=self.c0,
                                 nchains_local=self.Nl, nCR=nCR, ngamma=gamma_levels, nDEpairs=DEpairs, multitry=multitry,
                                 hardboundaries=int(bool(hardboundaries)), history_thin=self.thin,
-                                target_kind=int(target.kind), flags=(_cabi.FLAG_ALL_FLAT if self.all_flat else 0) | (_cabi.FLAG_GENERIC_KERNEL if generic_kernel else 0),
+                                target_kind=int(target.kind), flags=(_cabi.FLAG_ALL_FLAT if self.all_flat else 0) | (_cabi.FLAG_GENERIC_KERNEL if generic_kernel else 0)
+                                | (0 if window_kernel else _cabi.FLAG_NO_WINDOW_KERNEL),
                                 snooker=snooker, p_gamma_unity=p_gamma_unity, lamb=lamb, zeta=zeta, seed=int(seed) & (2 ** 64 - 1))
         ws = self.lib.dreamzs_adapt_workspace_bytes(C.byref(self.cfg))
         self.workspace = torch.zeros(max(int(ws), 8) // 8 + 1, **f64)
@@ -155,7 +160,9 @@ class DreamEngine:
                               last_like=p(self.last_like), cr_probs=p(self.cr_probs), gamma_probs=p(self.gamma_probs),
                               gamma_table=p(self.gamma_table), target_table=p(self.target_table),
                               prior_kind=p(self.prior_kind), prior_a=p(self.prior_a), prior_b=p(self.prior_b),
-                              mins=p(self.mins), maxs=p(self.maxs))
+                              mins=p(self.mins), maxs=p(self.maxs),
+                              gauss_Y=p(self.gauss_Y) if self.gauss_Y is not None else None,
+                              gauss_Q=p(self.gauss_Q) if self.gauss_Q is not None else None)
 
     def _ensure_capacity(self, rows):
         if self.Z is not None and self.Z.shape[0] >= rows:

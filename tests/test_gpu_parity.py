@@ -138,3 +138,43 @@ def test_gauss_kernel_equals_generic_kernel():
     np.testing.assert_array_equal(a[2], b[2])
     assert np.all(np.abs(a[1] - b[1]) <= logp_tol(b[1]))
     np.testing.assert_allclose(a[0], b[0], rtol=1e-10, atol=1e-11)
+
+
+def test_window_kernel_equals_generic_kernel():
+    """The dense-Gaussian window kernel (incremental quadratic form, batched draws, TMA-staged rows) consumes the
+    same random streams as the generic kernel: identical decisions, logp within tolerance, for any split of the
+    run into launches."""
+    from pydream_b200.engine import DreamEngine
+    rng = np.random.default_rng(78)
+    d, N, T = 100, 1031, 47      # N not a multiple of the chains-per-CTA tile
+    tgt = make_target(dict(kind='gaussian', d=d))
+    hist = rng.uniform(-5, 15, size=(2 * N + 5, d))
+    kw = dict(seed=10, snooker=.15, history_thin=7)
+    a = _run(DreamEngine(d, N, hist, hist[:N], tgt, **kw), T)
+    b = _run(DreamEngine(d, N, hist, hist[:N], tgt, generic_kernel=True, **kw), T)
+    c = _run(DreamEngine(d, N, hist, hist[:N], tgt, window_kernel=False, **kw), T)
+    for other in (b, c):
+        np.testing.assert_array_equal(a[2], other[2])
+        assert np.all(np.abs(a[1] - other[1]) <= logp_tol(other[1])), (np.abs(a[1] - other[1]) / logp_tol(other[1])).max()
+        np.testing.assert_allclose(a[0], other[0], rtol=1e-10, atol=1e-11)
+    eng = DreamEngine(d, N, hist, hist[:N], tgt, **kw)
+    parts = [_run(eng, n) for n in (1, 2, 3, 11, 30)]
+    for i in range(3):
+        np.testing.assert_array_equal(a[i], np.concatenate([p[i] for p in parts], axis=0))
+
+
+@pytest.mark.parametrize('d', [68, 97, 128])
+def test_window_kernel_dimensions(d):
+    """Row strides that are / are not multiples of 8 doubles, odd dimensions, the largest supported row."""
+    from oracle import c_oracle
+    from pydream_b200.engine import DreamEngine
+    rng = np.random.default_rng(d)
+    N, T = 50, 33
+    tgt = make_target(dict(kind='gaussian', d=d))
+    hist = rng.uniform(-5, 15, size=(2 * N + 3, d))
+    kw = dict(snooker=.2, history_thin=4)
+    ref = c_oracle.OracleSampler(d, N, hist, hist[:N], tgt.kind, tgt.table(), seed=3, nthreads=4, **kw).run(T)
+    states, logp, dec = _run(DreamEngine(d, N, hist, hist[:N], tgt, seed=3, **kw), T)
+    np.testing.assert_array_equal(dec, ref['decisions'])
+    assert np.all(np.abs(logp - ref['logp']) <= logp_tol(ref['logp']))
+    np.testing.assert_allclose(states, ref['states'], rtol=1e-10, atol=1e-11)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument('--target', default='gaussian')
     ap.add_argument('--multitry', type=int, default=1)
     ap.add_argument('--time', action='store_true', help='print CUDA-event timing of the run')
+    ap.add_argument('--phases', action='store_true', help='print the clock64 phase stamps of CTA 0 of the last window-kernel launch')
     a = ap.parse_args()
     import torch
     from pydream_b200 import targets
@@ -40,6 +41,10 @@ def main():
                       record_decisions=False, generic_kernel=a.generic)
     eng.run(11)
     torch.cuda.synchronize()
+    if a.phases:
+        import ctypes
+        buf = torch.zeros(64, dtype=torch.int64, device='cuda')
+        eng.lib.dreamzs_debug_set_phase_buffer(ctypes.c_void_p(buf.data_ptr()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.launches
     e0.record()
@@ -51,6 +56,13 @@ def main():
         print('%s d=%d N=%d: %d iterations in %.3f ms -> %.2f us/iter, %.1f M chain-steps/s, %d launches'
               % ('generic' if a.generic else 'auto', d, N, a.iters, ms, 1e3 * ms / a.iters, N * a.iters / ms / 1e3,
                  eng.launches - l0))
+
+
+    if a.phases:
+        t = buf.cpu().numpy()
+        n = int((t != 0).sum())
+        print('phase stamps (cycles since kernel entry, CTA 0 thread 0):', [int(v - t[0]) for v in t[1:n]])
+        print('deltas:', [int(t[i + 1] - t[i]) for i in range(n - 1)])
 
 
 if __name__ == '__main__':
