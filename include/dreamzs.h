@@ -147,6 +147,23 @@ int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state *st, void *
 int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                  int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream);
 
+/* The chain loop of _sample_dream (pydream/core.py:103-122) for iterations that need no host decision between
+ * them (no adaptation): iterations iter_begin .. iter_begin+niter-1 as one dreamzs_step launch per window, a
+ * window ending at an iteration t with t % history_thin == 0.  tr->trace_offset is the trace row of
+ * iter_begin.  After each appending launch `hook(user, first_row, nrows)` is called on the host (it may
+ * enqueue stream-ordered work, e.g. the all-gather of the other shards' rows; it must return 0); hook may be
+ * NULL when nchains_local == nchains_global.  *launches (optional) receives the number of kernel launches,
+ * *archive_rows_out (optional) the archive size after the run. */
+typedef int (*dreamzs_append_hook)(void *user, int64_t first_row, int64_t nrows);
+int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
+                int64_t iter_begin, int64_t niter, int64_t archive_rows, dreamzs_append_hook hook, void *user,
+                void *stream, int64_t *launches, int64_t *archive_rows_out);
+
+/* sampled_params / log_ps leave the device (pydream/core.py:81-86 returns them to the caller): stream-ordered
+ * copy of `height` rows of `width_bytes` from a pitched device block to a pitched (pinned) host block. */
+int dreamzs_copy_d2h_2d(void *dst_host, int64_t dst_pitch_bytes, const void *src_device, int64_t src_pitch_bytes,
+                        int64_t width_bytes, int64_t height, void *stream);
+
 /* Crossover-probability (and gamma-level) adaptation for ONE iteration of the burn-in
  * (estimate_crossover_probabilities, Dream.py:451-499; estimate_gamma_level_probs,
  * Dream.py:501-540; set_current_position_arr, Dream.py:424-449), as stream-ordered reduction

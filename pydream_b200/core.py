@@ -5,7 +5,8 @@ reference.  The multiprocessing pool (core.py:250-327) is replaced by `engine.Dr
 chains advance in lock-step inside one fused sm_100a kernel.  Extra, optional keywords (not in the
 reference): ``seed`` (Philox key; default drawn from the OS like the reference's unseeded runs),
 ``device``, ``group`` (torch.distributed process group: chains are sharded over its ranks and each
-rank returns the chains it owns), ``return_device`` (return device tensors instead of numpy lists).
+rank returns the chains it owns), ``return_device`` (return device tensors instead of numpy lists), ``stream_chunk`` (iterations per
+device->host chunk; samples stream to pinned host memory while sampling continues).
 """
 import os
 from datetime import datetime
@@ -56,6 +57,7 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
     device = kwargs.pop('device', None)
     group = kwargs.pop('group', None)
     return_device = kwargs.pop('return_device', False)
+    stream_chunk = kwargs.pop('stream_chunk', 256)
 
     if restart:
         if start == None:   # noqa: E711
@@ -137,12 +139,26 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
                       cr_probs=np.asarray(step_instance.CR_probabilities, dtype=np.float64),
                       gamma_probs=np.asarray(step_instance.gamma_probabilities, dtype=np.float64),
                       device=device, group=group, record_decisions=bool(verbose))
-    trace, logp, dec = eng.run(niterations)
+    import torch
+    acc_chunks = []
+    on_chunk = None
+    if verbose:
+        on_chunk = lambda dec, t0: acc_chunks.append((dec & 1).to(torch.float64).mean(dim=0))
+    if return_device:
+        trace, logp, dec = eng.run(niterations)
+        if verbose and dec is not None:
+            on_chunk(dec, 0)
+    else:
+        # samples stream to pinned host memory while sampling continues (torch's caching host allocator
+        # recycles the pinned blocks of earlier calls once their arrays have been dropped)
+        tr_host = torch.empty((eng.Nl, niterations, d), dtype=torch.float64, pin_memory=True)
+        lp_host = torch.empty((eng.Nl, niterations, 1), dtype=torch.float64, pin_memory=True)
+        eng.run_to_host(niterations, tr_host, lp_host, chunk_iters=stream_chunk, on_chunk=on_chunk)
     step_instance.CR_probabilities = eng.cr_probs.cpu().numpy()
     step_instance.gamma_probabilities = eng.gamma_probs.cpu().numpy()
 
-    if verbose and dec is not None:
-        _print_acceptance(dec, niterations, nverbose)
+    if verbose and acc_chunks:
+        _print_acceptance(torch.cat(acc_chunks), niterations, nverbose)
 
     # ---- history / adapted probabilities on disk when the archive is full (Dream.py:939-969)
     if step_instance.save_history and eng.rank == 0:
@@ -153,11 +169,6 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
 
     if return_device:
         return trace, logp
-    import torch
-    tr_host = torch.empty((eng.Nl, niterations, d), dtype=torch.float64, pin_memory=True)
-    lp_host = torch.empty((eng.Nl, niterations, 1), dtype=torch.float64, pin_memory=True)
-    tr_host.copy_(trace[:, :, :d], non_blocking=True)
-    lp_host.copy_(logp.unsqueeze(2), non_blocking=True)
     torch.cuda.current_stream(eng.device).synchronize()
     tr_np, lp_np = tr_host.numpy(), lp_host.numpy()
     sampled_params = [tr_np[c] for c in range(eng.Nl)]
@@ -165,12 +176,11 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
     return sampled_params, log_ps
 
 
-def _print_acceptance(dec, niterations, nverbose):
+def _print_acceptance(acc_mean, niterations, nverbose):
     """Acceptance-rate lines at the cadence of _sample_dream (pydream/core.py:104-112), averaged over chains
-    (the reference prints one line per chain process)."""
+    (the reference prints one line per chain process).  acc_mean: [T] mean acceptance per iteration (device)."""
     import torch
-    acc = (dec & 1).to(torch.float64)               # [Nl, T]
-    cum = torch.cumsum(acc.mean(dim=0), dim=0).cpu().numpy()
+    cum = torch.cumsum(acc_mean, dim=0).cpu().numpy()
     for iteration in range(0, niterations, max(int(nverbose), 1)):
         naccepts = cum[iteration - 1] if iteration > 0 else 0.0
         print('Iteration: ', iteration, ' acceptance rate: ', float(naccepts)/(iteration+1))

@@ -138,3 +138,46 @@ extern "C" int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, 
   P.all_flat = all_flat_hint(cfg);
   return dispatch(P, (cudaStream_t)stream);
 }
+
+// _sample_dream's loop (pydream/core.py:103-122) for the steady state (no adaptation): one launch per window.
+extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
+                           int64_t iter_begin, int64_t niter, int64_t archive_rows, dreamzs_append_hook hook,
+                           void *user, void *stream, int64_t *launches, int64_t *archive_rows_out) {
+  if (!cfg || niter < 0 || iter_begin < 0 || !tr) return DREAMZS_E_BADARG;
+  if (cfg->history_thin < 1) return DREAMZS_E_BADARG;
+  if (!hook && cfg->nchains_local != cfg->nchains_global) return DREAMZS_E_BADARG;   // other shards' rows need the hook
+  const int64_t thin = cfg->history_thin, end = iter_begin + niter;
+  dreamzs_trace w = *tr;
+  int64_t t = iter_begin, nl = 0;
+  while (t < end) {
+    const int64_t nxt = ((t + thin - 1) / thin) * thin;          // first appending iteration >= t
+    const int64_t n = (end < nxt + 1 ? end : nxt + 1) - t;
+    w.trace_offset = tr->trace_offset + (t - iter_begin);
+    int rc = dreamzs_step(cfg, st, &w, t, (int32_t)n, archive_rows, stream);
+    if (rc != DREAMZS_OK) return rc;
+    ++nl;
+    if ((t + n - 1) % thin == 0) {                               // record_history for every chain (Dream.py:919-938)
+      if (hook) {
+        rc = hook(user, archive_rows, cfg->nchains_global);
+        if (rc != DREAMZS_OK) return rc;
+      }
+      archive_rows += cfg->nchains_global;
+    }
+    t += n;
+  }
+  if (launches) *launches = nl;
+  if (archive_rows_out) *archive_rows_out = archive_rows;
+  return DREAMZS_OK;
+}
+
+// sampled_params / log_ps leave the device (core.py:81-86): strided device block -> strided host block
+extern "C" int dreamzs_copy_d2h_2d(void *dst_host, int64_t dst_pitch_bytes, const void *src_device, int64_t src_pitch_bytes,
+                                   int64_t width_bytes, int64_t height, void *stream) {
+  if (!dst_host || !src_device || width_bytes < 0 || height < 0 || dst_pitch_bytes < width_bytes || src_pitch_bytes < width_bytes)
+    return DREAMZS_E_BADARG;
+  if (width_bytes == 0 || height == 0) return DREAMZS_OK;
+  const cudaError_t e = cudaMemcpy2DAsync(dst_host, (size_t)dst_pitch_bytes, src_device, (size_t)src_pitch_bytes, (size_t)width_bytes,
+                                          (size_t)height, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return DREAMZS_E_LAUNCH; }
+  return DREAMZS_OK;
+}

@@ -105,4 +105,21 @@ __device__ __forceinline__ int gsum_int(int v, unsigned gmask) {
   return v;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device): `cache` is a per-kernel array
+// indexed by device ordinal (the launchers keep it in a function-local static).
+template <typename K>
+inline int ensure_dynamic_smem(K kern, size_t smem, size_t (&cache)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return DREAMZS_E_LAUNCH; }
+  dev &= 63;
+  if (smem > cache[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return DREAMZS_E_LAUNCH;
+    }
+    cache[dev] = smem;
+  }
+  return DREAMZS_OK;
+}
+
 }  // namespace dreamzs

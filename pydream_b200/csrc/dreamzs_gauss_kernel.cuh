@@ -427,10 +427,8 @@ template <int TC>
 int launch_gauss(const StepParams &P, cudaStream_t stream) {
   const size_t smem = gauss_smem_bytes(P.cfg, TC);
   auto kern = dreamzs_gauss_kernel<TC>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return DREAMZS_E_LAUNCH;
-  }
+  static size_t smem_set[64] = {0};
+  if (ensure_dynamic_smem(kern, smem, smem_set) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
   const int grid = (P.cfg.nchains_local + TC - 1) / TC;
   kern<<<grid, GK_THREADS, smem, stream>>>(P);
   return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;

@@ -572,10 +572,8 @@ int launch_gwin(StepParams &P, cudaStream_t stream) {
   if (P.gw_nb == 0) return DREAMZS_E_UNSUPPORTED;
   P.gw_append = (P.iter_begin + P.niter - 1) % P.cfg.history_thin == 0 ? 1 : 0;
   auto kern = dreamzs_gwin_kernel<TC>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return DREAMZS_E_LAUNCH;
-  }
+  static size_t smem_set[64] = {0};
+  if (ensure_dynamic_smem(kern, smem, smem_set) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
   const int grid = (P.cfg.nchains_local + TC - 1) / TC;
   kern<<<grid, GW_THREADS, smem, stream>>>(P);
   return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;

@@ -613,10 +613,8 @@ int launch_step(const StepParams &P, int threads, size_t smem, cudaStream_t stre
   const int grid = (P.cfg.nchains_local + chains_per_cta - 1) / chains_per_cta;
   auto kern = dreamzs_step_kernel<G, R>;
   if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return DREAMZS_E_LAUNCH;
-    }
+    static size_t smem_set[64] = {0};
+    if (ensure_dynamic_smem(kern, smem, smem_set) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
   }
   kern<<<grid, threads, smem, stream>>>(P);
   return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;

@@ -146,6 +146,7 @@ class DreamEngine:
         self.colsum, self.colsq = torch.zeros(d, **f64), torch.zeros(d, **f64)
         self.partial = torch.zeros(2 * nCR + 2 * gamma_levels, **f64)
         self.launches = 0
+        self._hook = _cabi.APPEND_HOOK(self._append_hook)
         self._state()
         _cabi.check(self.lib.dreamzs_init_logp(C.byref(self.cfg), C.byref(self.st), self._stream()), 'dreamzs_init_logp')
         self.launches += 1
@@ -169,9 +170,15 @@ class DreamEngine:
             return
         Z = torch.zeros((rows, self.ld), dtype=torch.float64, device=self.device)
         if self.Z is None:
-            h = np.zeros((self.nseed, self.ld))
-            h[:, :self.d] = self._hist_host
-            Z[:self.nseed] = torch.from_numpy(h).to(self.device)
+            # seed rows: one host->device copy of the caller's array (asynchronous when it lives in pinned memory),
+            # padded to the row stride on the device
+            h = torch.from_numpy(np.ascontiguousarray(self._hist_host))
+            hd = h.to(self.device, non_blocking=h.is_pinned())
+            if self.ld == self.d:
+                Z[:self.nseed] = hd
+            else:
+                Z[:self.nseed, :self.d] = hd
+            self._hist_host = None
         else:
             Z[:self.Z.shape[0]] = self.Z
         self.Z = Z
@@ -195,27 +202,103 @@ class DreamEngine:
         if decisions is None and self.record_decisions:
             decisions = torch.empty((self.Nl, niter), dtype=torch.int32, device=dev)
         self._ensure_capacity(self.archive_rows + appends_in(self.iter, niter, self.thin) * self.N)
+        self._advance(niter, trace, logp, decisions)
+        return trace, logp, decisions
+
+    def _advance(self, niter, trace, logp, decisions):
+        """`niter` iterations into trace rows 0..niter-1 of the given buffers ([Nl, >=niter, ld] etc.).
+        Burn-in iterations with adaptation run one launch each with the reduction kernels in between
+        (Dream.py:364-401); everything else goes through the native window loop dreamzs_run."""
         adapting = self.adapt_crossover or self.adapt_gamma
-        if adapting and self.iter <= self.crossover_burnin:
-            self._x_entry = self.X.clone()
-        single_until = self.crossover_burnin if adapting else -1
+        T_ = trace.shape[1]
         tr = _cabi.Trace(trace=trace.data_ptr(), trace_logp=logp.data_ptr(),
-                         decisions=decisions.data_ptr() if decisions is not None else None, trace_iters=niter, trace_offset=0)
-        t_first = self.iter
+                         decisions=decisions.data_ptr() if decisions is not None else None, trace_iters=T_, trace_offset=0)
         stream = self._stream()
         cfg, st = C.byref(self.cfg), C.byref(self.st)
-        for (t, n) in plan_segments(self.iter, niter, self.thin, single_until):
+        t_first, end = self.iter, self.iter + niter
+        t = self.iter
+        if adapting and t <= self.crossover_burnin:
+            self._x_entry = self.X.clone()
+            while t < end and t <= self.crossover_burnin:
+                tr.trace_offset = t - t_first
+                rc = self.lib.dreamzs_step(cfg, st, C.byref(tr), t, 1, self.archive_rows, stream)
+                _cabi.check(rc, 'dreamzs_step')
+                self.launches += 1
+                if (10 < t < self.crossover_burnin) or t == self.crossover_burnin:
+                    self._adapt(trace, decisions, t - t_first, t == self.crossover_burnin)
+                if t % self.thin == 0:
+                    self._publish_append()
+                t += 1
+        if t < end:
             tr.trace_offset = t - t_first
-            rc = self.lib.dreamzs_step(cfg, st, C.byref(tr), t, n, self.archive_rows, stream)
-            _cabi.check(rc, 'dreamzs_step')
-            self.launches += 1
-            last = t + n - 1
-            if adapting and n == 1 and ((10 < last < self.crossover_burnin) or last == self.crossover_burnin):
-                self._adapt(trace, decisions, last - t_first, last == self.crossover_burnin)
-            if last % self.thin == 0:
-                self._publish_append()
-        self.iter += niter
-        return trace, logp, decisions
+            nl, rows = C.c_int64(0), C.c_int64(0)
+            hook = self._hook if self.world > 1 else _cabi.APPEND_HOOK()
+            rc = self.lib.dreamzs_run(cfg, st, C.byref(tr), t, end - t, self.archive_rows, hook, None, stream,
+                                      C.byref(nl), C.byref(rows))
+            _cabi.check(rc, 'dreamzs_run')
+            self.launches += int(nl.value)
+            self.count = int(rows.value) - self.nseed
+        self.iter = end
+
+    def run_to_host(self, niter, out_params, out_logp, chunk_iters=256, on_chunk=None):
+        """Run `niter` iterations and stream the samples to host memory while sampling continues.
+        out_params: pinned host tensor [Nl, niter, d]; out_logp: pinned host tensor [Nl, niter] (or [Nl, niter, 1]).
+        The run is cut into chunks of `chunk_iters` iterations written to two alternating device buffers; each
+        finished chunk leaves on a copy stream (pitched device->host copies through the C ABI) while the next
+        one is being sampled.  `on_chunk(decisions_chunk, t0)` (optional) sees each chunk's decision words."""
+        niter, d, ld, Nl = int(niter), self.d, self.ld, self.Nl
+        dev = self.device
+        Tc = max(1, min(int(chunk_iters), niter))
+        self._ensure_capacity(self.archive_rows + appends_in(self.iter, niter, self.thin) * self.N)
+        compute = torch.cuda.current_stream(dev)
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy = self._copy_stream
+        need_dec = self.record_decisions
+        bufs = []
+        for _ in range(2 if niter > Tc else 1):
+            bufs.append(dict(trace=torch.empty((Nl, Tc, ld), dtype=torch.float64, device=dev),
+                             logp=torch.empty((Nl, Tc), dtype=torch.float64, device=dev),
+                             dec=torch.empty((Nl, Tc), dtype=torch.int32, device=dev) if need_dec else None,
+                             packed=torch.empty((Nl, Tc, d), dtype=torch.float64, device=dev) if ld != d else None,
+                             filled=torch.cuda.Event(), drained=None))
+        hp, hl = out_params.data_ptr(), out_logp.data_ptr()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        t0, k = 0, 0
+        while t0 < niter:
+            n = min(Tc, niter - t0)
+            b = bufs[k % len(bufs)]
+            if b['drained'] is not None:
+                compute.wait_event(b['drained'])          # the copy of the chunk that used this buffer has finished
+            self._advance(n, b['trace'], b['logp'], b['dec'])
+            src, spitch = b['trace'], Tc * ld * 8
+            if ld != d:                                   # strip the row padding on the device
+                b['packed'][:, :n].copy_(b['trace'][:, :n, :d])
+                src, spitch = b['packed'], Tc * d * 8
+            if on_chunk is not None and b['dec'] is not None:
+                on_chunk(b['dec'][:, :n], t0)
+            b['filled'].record(compute)
+            copy.wait_event(b['filled'])
+            cs = C.c_void_p(copy.cuda_stream)
+            _cabi.check(self.lib.dreamzs_copy_d2h_2d(C.c_void_p(hp + t0 * d * 8), niter * d * 8, p(src), spitch, n * d * 8, Nl, cs),
+                        'dreamzs_copy_d2h_2d')
+            _cabi.check(self.lib.dreamzs_copy_d2h_2d(C.c_void_p(hl + t0 * 8), niter * 8, p(b['logp']), Tc * 8, n * 8, Nl, cs),
+                        'dreamzs_copy_d2h_2d')
+            b['drained'] = torch.cuda.Event()
+            b['drained'].record(copy)
+            t0 += n
+            k += 1
+        compute.wait_stream(copy)                          # results are complete once the caller syncs its stream
+
+    def _append_hook(self, user, first_row, nrows):
+        """dreamzs_append_hook: all-gather the rows the other shards appended (enqueued on the current stream)."""
+        try:
+            allgather_rows(self.Z[first_row:first_row + nrows], self.c0, self.Nl, self.group)
+            return 0
+        except Exception:      # never let an exception cross the C ABI
+            import traceback
+            traceback.print_exc()
+            return _cabi.E_LAUNCH
 
     def _publish_append(self):
         """record_history for the whole sweep: the kernel wrote the local rows; gather the others."""
