@@ -146,12 +146,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
       // ---- S: scalar draws and archive rows of the warp's columns, one Philox block per lane:
       //      lanes 0-5: snooker, CR, gamma level, gamma unity (Dream.py:542-599, 615), first two
       //      np.random.uniform() (snooker gamma :618 / Metropolis :993); lanes 8-10: random.sample calls 0-2
-      int c_snk[GW_MAXCOLW], c_cr[GW_MAXCOLW], c_lvl[GW_MAXCOLW], c_unity[GW_MAXCOLW];
-      double c_lu[GW_MAXCOLW], c_u0[GW_MAXCOLW];
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < GW_MAXCOLW; ++k) {
         const int col = warp + GW_WARPS * k;
-        c_snk[k] = c_cr[k] = c_lvl[k] = c_unity[k] = 0; c_lu[k] = c_u0[k] = 0.0;
         const int itb = col / TC, ch = col - itb * TC;
         if (col < nbc && ch < nch) {
           const uint32_t iter = (uint32_t)(P.iter_begin + done + itb);
@@ -176,14 +173,15 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
           }
           const double lg = log(u);
           if (k == 0) GW_STAMP();   // s1: philox, multinomial, log
-          const int snk = (s0 != 0u) && __shfl_sync(0xffffffffu, idx, 0) == 0;
-          c_snk[k] = snk;
-          c_cr[k] = __shfl_sync(0xffffffffu, idx, 1);
-          c_lvl[k] = __shfl_sync(0xffffffffu, idx, 2);
-          c_unity[k] = __shfl_sync(0xffffffffu, idx, 3);
-          c_u0[k] = __shfl_sync(0xffffffffu, u, 4);
-          const double lu0 = __shfl_sync(0xffffffffu, lg, 4), lu1 = __shfl_sync(0xffffffffu, lg, 5);
-          c_lu[k] = snk ? lu1 : lu0;
+          // decisions of the column -> meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set
+          // in V), 10 gamma-unity draw says "not unity"
+          const unsigned bal_snk = __ballot_sync(0xffffffffu, idx == 0);
+          const int snk = (s0 != 0u) && (bal_snk & 1u);
+          const int cr_s = __shfl_sync(0xffffffffu, idx, 1), lvl_s = __shfl_sync(0xffffffffu, idx, 2);
+          const int unity_s = __shfl_sync(0xffffffffu, idx, 3);
+          if (lane == 0) meta[col] = (uint32_t)cr_s | ((uint32_t)lvl_s << 4) | (snk ? 256u : 0u) | (unity_s != 0 ? 1024u : 0u);
+          if (lane == (snk ? 5 : 4)) logu[col] = lg;                               // Metropolis uniform: 2nd draw after a snooker gamma
+          if (lane == 4) gsn[col] = 1.2 + (2.2 - 1.2) * u;                         // snooker gamma, Dream.py:618
           if (k == 0) GW_STAMP();   // s2: shuffles
           // archive rows (sample_from_history, Dream.py:646-668), TMA-staged into the column's slots:
           //   DE      z_r1 -> J slot, z_r2 -> zeta slot;   snooker  z -> J slot, z1 -> W slot, z2 -> zeta slot
@@ -212,14 +210,15 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
       }
       GW_STAMP();   // +0: rows requested (warp 0)
       // ---- V: the columns (generate_proposal_points DE branch, Dream.py:688-726; snooker rows, :808-810)
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < GW_MAXCOLW; ++k) {
         const int col = warp + GW_WARPS * k;
         const int itb = col / TC, ch = col - itb * TC;
         if (col < nbc && ch < nch) {
           const uint32_t iter = (uint32_t)(P.iter_begin + done + itb);
           const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
-          const int snk = c_snk[k], cr_idx = c_cr[k], lvl_idx = c_lvl[k];
+          const uint32_t mt = meta[col];
+          const int snk = (mt >> 8) & 1, cr_idx = mt & 15, lvl_idx = (mt >> 4) & 15;
           double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
           if (!snk) {
             double zeta[4] = {0, 0, 0, 0}, e[4] = {1, 1, 1, 1};
@@ -247,11 +246,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
             }
             dprime = __reduce_add_sync(0xffffffffu, dprime);
             double gamma = 1.0;
-            if (c_unity[k] != 0) gamma = gam[lvl_idx * d + (dprime >= 1 ? dprime - 1 : d - 1)];
-            if (lane == 0) {
-              meta[col] = (uint32_t)cr_idx | ((uint32_t)lvl_idx << 4) | ((gamma == 1.0) ? 512u : 0u);
-              logu[col] = c_lu[k];
-            }
+            if (mt & 1024u) gamma = gam[lvl_idx * d + (dprime >= 1 ? dprime - 1 : d - 1)];
+            if (lane == 0 && gamma == 1.0) meta[col] = mt | 512u;
             mbar_wait(mbar + col, parity);
             if (own) {
               const double2 a01 = *reinterpret_cast<const double2 *>(js), a23 = *reinterpret_cast<const double2 *>(js + 2);
@@ -270,12 +266,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
               *reinterpret_cast<double2 *>(ws) = make_double2(dl[0], dl[1]); *reinterpret_cast<double2 *>(ws + 2) = make_double2(dl[2], dl[3]);
             }
           } else {
-            if (lane == 0) {
-              const double gamma = 1.2 + (2.2 - 1.2) * c_u0[k];
-              meta[col] = 256u | (uint32_t)cr_idx | ((uint32_t)lvl_idx << 4) | ((gamma == 1.0) ? 512u : 0u);
-              gsn[col] = gamma;
-              logu[col] = c_lu[k];
-            }
+            if (lane == 0 && gsn[col] == 1.0) meta[col] = mt | 512u;
             mbar_wait(mbar + col, parity);
             if (own) {
               const double2 z01 = *reinterpret_cast<const double2 *>(js), z23 = *reinterpret_cast<const double2 *>(js + 2);
