@@ -90,7 +90,7 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
         # a path, as in the reference, or (extension) the array itself
         hf = step_instance.history_file
         old_history = hf if isinstance(hf, np.ndarray) else np.load(hf)
-        len_old_history = len(old_history.flatten())
+        len_old_history = int(np.asarray(old_history).size)
         step_instance.nseedchains = len_old_history/d
     min_nseedchains = 2*len(step_instance.DEpairs)*nchains
     if step_instance.nseedchains < min_nseedchains:
@@ -128,6 +128,9 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
     if seed is None:
         seed = int.from_bytes(os.urandom(8), 'little')
 
+    import time
+    timing = os.environ.get('DREAMZS_TIMING')
+    t_a = time.perf_counter()
     from .engine import DreamEngine   # imports torch; fails loudly without CUDA / libdreamzs.so
     eng = DreamEngine(d, nchains, history, starts, likelihood, prior_kind, prior_a, prior_b, seed=seed,
                       nCR=step_instance.nCR, gamma_levels=step_instance.ngamma, DEpairs=len(step_instance.DEpairs),
@@ -138,8 +141,9 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
                       crossover_burnin=step_instance.crossover_burnin,
                       cr_probs=np.asarray(step_instance.CR_probabilities, dtype=np.float64),
                       gamma_probs=np.asarray(step_instance.gamma_probabilities, dtype=np.float64),
-                      device=device, group=group, record_decisions=bool(verbose))
+                      device=device, group=group, record_decisions=bool(verbose), reserve_iters=niterations)
     import torch
+    t_b = time.perf_counter()
     acc_chunks = []
     on_chunk = None
     if verbose:
@@ -154,6 +158,7 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
         tr_host = torch.empty((eng.Nl, niterations, d), dtype=torch.float64, pin_memory=True)
         lp_host = torch.empty((eng.Nl, niterations, 1), dtype=torch.float64, pin_memory=True)
         eng.run_to_host(niterations, tr_host, lp_host, chunk_iters=stream_chunk, on_chunk=on_chunk)
+    t_c = time.perf_counter()
     step_instance.CR_probabilities = eng.cr_probs.cpu().numpy()
     step_instance.gamma_probabilities = eng.gamma_probs.cpu().numpy()
 
@@ -170,9 +175,13 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
     if return_device:
         return trace, logp
     torch.cuda.current_stream(eng.device).synchronize()
+    t_d = time.perf_counter()
     tr_np, lp_np = tr_host.numpy(), lp_host.numpy()
     sampled_params = [tr_np[c] for c in range(eng.Nl)]
     log_ps = [lp_np[c] for c in range(eng.Nl)]
+    if timing:
+        print('run_dream stages (ms): engine+upload %.2f, enqueue %.2f, drain %.2f, lists %.2f'
+              % (1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (t_d - t_c), 1e3 * (time.perf_counter() - t_d)))
     return sampled_params, log_ps
 
 

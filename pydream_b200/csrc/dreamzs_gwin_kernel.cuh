@@ -142,145 +142,174 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
     const bool do_refresh = P.gw_refresh && batch == 0;
     const uint32_t parity = (uint32_t)(batch & 1);
     // ================================================================ G: generation (warp per column)
+    // A warp owns the columns warp, warp+16, warp+32 of the batch and works on them in lock-step (straight-line
+    // code over the three: the long dependent chains of Philox / log / Box-Muller interleave).
     {
-      // ---- S: scalar draws and archive rows of the warp's columns, one Philox block per lane:
+      int colk[GW_MAXCOLW];
+      bool valid[GW_MAXCOLW];
+      uint32_t iterk[GW_MAXCOLW], chk[GW_MAXCOLW];
+#pragma unroll
+      for (int k = 0; k < GW_MAXCOLW; ++k) {
+        const int col = warp + GW_WARPS * k;
+        const int itb = col / TC, ch = col - itb * TC;
+        valid[k] = col < nbc && ch < nch;
+        colk[k] = valid[k] ? col : 0;
+        iterk[k] = (uint32_t)(P.iter_begin + done + (valid[k] ? itb : 0));
+        chk[k] = (uint32_t)(P.cfg.chain_begin + cta_chain0 + (valid[k] ? ch : 0));
+      }
+      // ---- S: scalar draws and archive rows, one Philox block per lane:
       //      lanes 0-5: snooker, CR, gamma level, gamma unity (Dream.py:542-599, 615), first two
       //      np.random.uniform() (snooker gamma :618 / Metropolis :993); lanes 8-10: random.sample calls 0-2
-#pragma unroll 1
-      for (int k = 0; k < GW_MAXCOLW; ++k) {
-        const int col = warp + GW_WARPS * k;
-        const int itb = col / TC, ch = col - itb * TC;
-        if (col < nbc && ch < nch) {
-          const uint32_t iter = (uint32_t)(P.iter_begin + done + itb);
-          const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
-          uint32_t call = 0, st = ST_MULTINOMIAL;
-          const double *pp = probs + 24;
-          int n = 2;
-          if (lane == 1) { call = s0; pp = probs; n = P.cfg.nCR; }
-          else if (lane == 2) { call = s0 + 1; pp = probs + 16; n = P.cfg.ngamma; }
-          else if (lane == 3) { call = s0 + 2; pp = probs + 26; }
-          else if (lane == 4) { st = ST_UNIFORM_SCAL; }
-          else if (lane == 5) { call = 1; st = ST_UNIFORM_SCAL; }
-          else if (lane >= 8) { call = (uint32_t)(lane - 8) & 3u; st = ST_SAMPLE; }
-          const uint4 w = philox4x32(0u, (call << 3) | st, iter, c_global, k0, k1);
-          const double u = u53_of(w.x, w.y);
-          double acc = 0.0;
-          int idx = n - 1;
-          bool found = false;
-          for (int j = 0; j < n; ++j) {
-            acc = acc + pp[j];
-            if (!found && u < acc) { idx = j; found = true; }
+      {
+        uint32_t call = 0, st = ST_MULTINOMIAL;
+        const double *pp = probs + 24;
+        int n = 2;
+        if (lane == 1) { call = s0; pp = probs; n = P.cfg.nCR; }
+        else if (lane == 2) { call = s0 + 1; pp = probs + 16; n = P.cfg.ngamma; }
+        else if (lane == 3) { call = s0 + 2; pp = probs + 26; }
+        else if (lane == 4) { st = ST_UNIFORM_SCAL; }
+        else if (lane == 5) { call = 1; st = ST_UNIFORM_SCAL; }
+        else if (lane >= 8) { call = (uint32_t)(lane - 8) & 3u; st = ST_SAMPLE; }
+        const int nmax = max(2, max(P.cfg.nCR, P.cfg.ngamma));
+        uint4 w[GW_MAXCOLW];
+        double u[GW_MAXCOLW], acc[GW_MAXCOLW], lg[GW_MAXCOLW];
+        int idx[GW_MAXCOLW];
+#pragma unroll
+        for (int k = 0; k < GW_MAXCOLW; ++k) w[k] = philox4x32(0u, (call << 3) | st, iterk[k], chk[k], k0, k1);
+#pragma unroll
+        for (int k = 0; k < GW_MAXCOLW; ++k) { u[k] = u53_of(w[k].x, w[k].y); acc[k] = 0.0; idx[k] = n - 1; }
+        unsigned found = 0;
+        for (int j = 0; j < nmax; ++j) {
+          const double pj = j < n ? pp[j] : 0.0;
+#pragma unroll
+          for (int k = 0; k < GW_MAXCOLW; ++k) {
+            acc[k] = acc[k] + pj;
+            if (j < n && !((found >> k) & 1u) && u[k] < acc[k]) { idx[k] = j; found |= 1u << k; }
           }
-          const double lg = log(u);
-          if (k == 0) GW_STAMP();   // s1: philox, multinomial, log
+        }
+#pragma unroll
+        for (int k = 0; k < GW_MAXCOLW; ++k) lg[k] = log(u[k]);
+        GW_STAMP();   // s1: philox, multinomial, log
+#pragma unroll
+        for (int k = 0; k < GW_MAXCOLW; ++k) {
           // decisions of the column -> meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set
           // in V), 10 gamma-unity draw says "not unity"
-          const unsigned bal_snk = __ballot_sync(0xffffffffu, idx == 0);
+          const unsigned bal_snk = __ballot_sync(0xffffffffu, idx[k] == 0);
           const int snk = (s0 != 0u) && (bal_snk & 1u);
-          const int cr_s = __shfl_sync(0xffffffffu, idx, 1), lvl_s = __shfl_sync(0xffffffffu, idx, 2);
-          const int unity_s = __shfl_sync(0xffffffffu, idx, 3);
-          if (lane == 0) meta[col] = (uint32_t)cr_s | ((uint32_t)lvl_s << 4) | (snk ? 256u : 0u) | (unity_s != 0 ? 1024u : 0u);
-          if (lane == (snk ? 5 : 4)) logu[col] = lg;                               // Metropolis uniform: 2nd draw after a snooker gamma
-          if (lane == 4) gsn[col] = 1.2 + (2.2 - 1.2) * u;                         // snooker gamma, Dream.py:618
-          if (k == 0) GW_STAMP();   // s2: shuffles
+          const int cr_s = __shfl_sync(0xffffffffu, idx[k], 1), lvl_s = __shfl_sync(0xffffffffu, idx[k], 2);
+          const int unity_s = __shfl_sync(0xffffffffu, idx[k], 3);
           // archive rows (sample_from_history, Dream.py:646-668), TMA-staged into the column's slots:
           //   DE      z_r1 -> J slot, z_r2 -> zeta slot;   snooker  z -> J slot, z1 -> W slot, z2 -> zeta slot
-          int64_t r0 = (int64_t)(((uint64_t)w.x * (uint64_t)M) >> 32);
-          int64_t r1 = (int64_t)(((uint64_t)w.y * (uint64_t)(M - 1)) >> 32);
+          int64_t r0 = (int64_t)(((uint64_t)w[k].x * (uint64_t)M) >> 32);
+          int64_t r1 = (int64_t)(((uint64_t)w[k].y * (uint64_t)(M - 1)) >> 32);
           if (r1 >= r0) r1 += 1;
-          if (lane == 8) {
-            fence_proxy_async();   // earlier generic-proxy accesses of the slots are ordered before the async writes
-            mbar_expect_tx(mbar + col, row_bytes * (snk ? 3u : 2u));
-          }
-          __syncwarp();
-          if (k == 0) GW_STAMP();   // s3: fence + expect_tx
-          double *js = Jc + (size_t)col * ld, *zs = Zc + (size_t)col * ld, *ws = Wc + (size_t)col * ld;
-          if (!snk) {
+          if (valid[k]) {
+            const int col = colk[k];
+            if (lane == 0) meta[col] = (uint32_t)cr_s | ((uint32_t)lvl_s << 4) | (snk ? 256u : 0u) | (unity_s != 0 ? 1024u : 0u);
+            if (lane == (snk ? 5 : 4)) logu[col] = lg[k];                            // Metropolis uniform: 2nd draw after a snooker gamma
+            if (lane == 4) gsn[col] = 1.2 + (2.2 - 1.2) * u[k];                      // snooker gamma, Dream.py:618
             if (lane == 8) {
-              tma_load_row(js, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
-              tma_load_row(zs, P.st.Z + (size_t)r1 * ld, row_bytes, mbar + col);
+              fence_proxy_async();   // earlier generic-proxy accesses of the slots are ordered before the async writes
+              mbar_expect_tx(mbar + col, row_bytes * (snk ? 3u : 2u));
             }
-          } else if (lane >= 8 && lane <= 10) {
-            fence_proxy_async();
-            tma_load_row(lane == 8 ? js : lane == 9 ? ws : zs, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
+            __syncwarp();
+            double *js = Jc + (size_t)col * ld, *zs = Zc + (size_t)col * ld, *ws = Wc + (size_t)col * ld;
+            if (!snk) {
+              if (lane == 8) {
+                tma_load_row(js, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
+                tma_load_row(zs, P.st.Z + (size_t)r1 * ld, row_bytes, mbar + col);
+              }
+            } else if (lane >= 8 && lane <= 10) {
+              fence_proxy_async();
+              tma_load_row(lane == 8 ? js : lane == 9 ? ws : zs, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
+            }
           }
-          __syncwarp();
-          if (k == 0) GW_STAMP();   // s4: TMA issued
         }
+        __syncwarp();
       }
       GW_STAMP();   // +0: rows requested (warp 0)
-      // ---- V: the columns (generate_proposal_points DE branch, Dream.py:688-726; snooker rows, :808-810)
-#pragma unroll 1
-      for (int k = 0; k < GW_MAXCOLW; ++k) {
-        const int col = warp + GW_WARPS * k;
-        const int itb = col / TC, ch = col - itb * TC;
-        if (col < nbc && ch < nch) {
-          const uint32_t iter = (uint32_t)(P.iter_begin + done + itb);
-          const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
-          const uint32_t mt = meta[col];
-          const int snk = (mt >> 8) & 1, cr_idx = mt & 15, lvl_idx = (mt >> 4) & 15;
-          double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
-          if (!snk) {
-            double zeta[4] = {0, 0, 0, 0}, e[4] = {1, 1, 1, 1};
-            unsigned reset = 15u;
-            int dprime = 0;
-            if (own && i0 < d) {
-              double nz[4];
-              normal4(philox4x32((uint32_t)lane, (0u << 3) | ST_NORMAL, iter, c_global, k0, k1), nz);
-              const uint4 we = philox4x32((uint32_t)lane, (0u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
-              const uint4 wu = philox4x32((uint32_t)lane, (1u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
-              const uint32_t wev[4] = {we.x, we.y, we.z, we.w}, wuv[4] = {wu.x, wu.y, wu.z, wu.w};
-              // U = w 2^-32 exactly, so U < CR <=> w < ceil(CR 2^32) and U > CR <=> w > floor(CR 2^32)
-              const double CRs = ((double)(cr_idx + 1) / (double)P.cfg.nCR) * 4294967296.0;
-              const uint64_t t_lt = (uint64_t)ceil(CRs), t_gt = (uint64_t)floor(CRs);
-              reset = 0;
+      // ---- V: the columns (generate_proposal_points DE branch, Dream.py:688-726; snooker rows, :808-810).
+      //      The DE variates are drawn for every column (a snooker column, 1 in 10, discards them).
+      {
+        double zeta[GW_MAXCOLW][4], e[GW_MAXCOLW][4];
+        unsigned reset[GW_MAXCOLW];
+        int dprime[GW_MAXCOLW];
+        uint32_t mt[GW_MAXCOLW];
+        const bool act = own && i0 < d;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                zeta[j] = 0.0 + P.cfg.zeta * nz[j];
-                e[j] = (-P.cfg.lamb + (P.cfg.lamb - (-P.cfg.lamb)) * u32_of(wev[j])) + 1;
-                if (i0 + j < d) {
-                  dprime += ((uint64_t)wuv[j] < t_lt);
-                  if ((uint64_t)wuv[j] > t_gt) reset |= 1u << j;
-                } else reset |= 1u << j;
-              }
-            }
-            dprime = __reduce_add_sync(0xffffffffu, dprime);
-            double gamma = 1.0;
-            if (mt & 1024u) gamma = gam[lvl_idx * d + (dprime >= 1 ? dprime - 1 : d - 1)];
-            if (lane == 0 && gamma == 1.0) meta[col] = mt | 512u;
-            mbar_wait(mbar + col, parity);
-            if (own) {
-              const double2 a01 = *reinterpret_cast<const double2 *>(js), a23 = *reinterpret_cast<const double2 *>(js + 2);
-              const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
-              const double diff[4] = {a01.x - b01.x, a01.y - b01.y, a23.x - b23.x, a23.y - b23.y};
-              double J[4], zt[4], dl[4];
+        for (int k = 0; k < GW_MAXCOLW; ++k) mt[k] = meta[colk[k]];
+        uint4 wn[GW_MAXCOLW], we[GW_MAXCOLW], wu[GW_MAXCOLW];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const bool keep = !((reset >> j) & 1u);
-                J[j] = keep ? (e[j] * gamma) * diff[j] : 0.0;
-                zt[j] = keep ? zeta[j] : 0.0;
-                dl[j] = J[j] + zt[j];
-              }
-              *reinterpret_cast<double2 *>(js) = make_double2(J[0], J[1]); *reinterpret_cast<double2 *>(js + 2) = make_double2(J[2], J[3]);
-              *reinterpret_cast<double2 *>(zs) = make_double2(zt[0], zt[1]); *reinterpret_cast<double2 *>(zs + 2) = make_double2(zt[2], zt[3]);
-              *reinterpret_cast<double2 *>(ws) = make_double2(dl[0], dl[1]); *reinterpret_cast<double2 *>(ws + 2) = make_double2(dl[2], dl[3]);
-            }
-          } else {
-            if (lane == 0 && gsn[col] == 1.0) meta[col] = mt | 512u;
-            mbar_wait(mbar + col, parity);
-            if (own) {
-              const double2 z01 = *reinterpret_cast<const double2 *>(js), z23 = *reinterpret_cast<const double2 *>(js + 2);
-              const double2 a01 = *reinterpret_cast<const double2 *>(ws), a23 = *reinterpret_cast<const double2 *>(ws + 2);
-              const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
-              *reinterpret_cast<double2 *>(zs) = make_double2(a01.x - b01.x, a01.y - b01.y);
-              *reinterpret_cast<double2 *>(zs + 2) = make_double2(a23.x - b23.x, a23.y - b23.y);
-              *reinterpret_cast<double2 *>(ws) = z01; *reinterpret_cast<double2 *>(ws + 2) = z23;
-            }
+        for (int k = 0; k < GW_MAXCOLW; ++k) {
+          wn[k] = philox4x32((uint32_t)lane, (0u << 3) | ST_NORMAL, iterk[k], chk[k], k0, k1);
+          we[k] = philox4x32((uint32_t)lane, (0u << 3) | ST_UNIFORM_VEC, iterk[k], chk[k], k0, k1);
+          wu[k] = philox4x32((uint32_t)lane, (1u << 3) | ST_UNIFORM_VEC, iterk[k], chk[k], k0, k1);
+        }
+#pragma unroll
+        for (int k = 0; k < GW_MAXCOLW; ++k) {
+          double nz[4];
+          normal4(wn[k], nz);
+          const uint32_t wev[4] = {we[k].x, we[k].y, we[k].z, we[k].w}, wuv[4] = {wu[k].x, wu[k].y, wu[k].z, wu[k].w};
+          // U = w 2^-32 exactly, so U < CR <=> w < ceil(CR 2^32) and U > CR <=> w > floor(CR 2^32)
+          const double CRs = ((double)((mt[k] & 15u) + 1u) / (double)P.cfg.nCR) * 4294967296.0;
+          const uint64_t t_lt = (uint64_t)ceil(CRs), t_gt = (uint64_t)floor(CRs);
+          reset[k] = 0; dprime[k] = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            zeta[k][j] = 0.0 + P.cfg.zeta * nz[j];
+            e[k][j] = (-P.cfg.lamb + (P.cfg.lamb - (-P.cfg.lamb)) * u32_of(wev[j])) + 1;
+            const bool in = act && i0 + j < d;
+            dprime[k] += (in && (uint64_t)wuv[j] < t_lt) ? 1 : 0;
+            if (!in || (uint64_t)wuv[j] > t_gt) reset[k] |= 1u << j;
           }
-        } else if (col < nbc && own) {
-          // column of a chain slot past the end of the shard: keep its product finite
-          double *ws = Wc + (size_t)col * ld + i0;
-          *reinterpret_cast<double2 *>(ws) = make_double2(0.0, 0.0); *reinterpret_cast<double2 *>(ws + 2) = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < GW_MAXCOLW; ++k) dprime[k] = __reduce_add_sync(0xffffffffu, dprime[k]);
+        GW_STAMP();   // v1: variates
+#pragma unroll
+        for (int k = 0; k < GW_MAXCOLW; ++k) {
+          const int col = colk[k];
+          const int snk = (mt[k] >> 8) & 1, lvl_idx = (mt[k] >> 4) & 15;
+          double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
+          if (valid[k]) {
+            if (!snk) {
+              double gamma = 1.0;
+              if (mt[k] & 1024u) gamma = gam[lvl_idx * d + (dprime[k] >= 1 ? dprime[k] - 1 : d - 1)];
+              if (lane == 0 && gamma == 1.0) meta[col] = mt[k] | 512u;
+              mbar_wait(mbar + col, parity);
+              if (own) {
+                const double2 a01 = *reinterpret_cast<const double2 *>(js), a23 = *reinterpret_cast<const double2 *>(js + 2);
+                const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
+                const double diff[4] = {a01.x - b01.x, a01.y - b01.y, a23.x - b23.x, a23.y - b23.y};
+                double J[4], zt[4], dl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const bool keep = !((reset[k] >> j) & 1u);
+                  J[j] = keep ? (e[k][j] * gamma) * diff[j] : 0.0;
+                  zt[j] = keep ? zeta[k][j] : 0.0;
+                  dl[j] = J[j] + zt[j];
+                }
+                *reinterpret_cast<double2 *>(js) = make_double2(J[0], J[1]); *reinterpret_cast<double2 *>(js + 2) = make_double2(J[2], J[3]);
+                *reinterpret_cast<double2 *>(zs) = make_double2(zt[0], zt[1]); *reinterpret_cast<double2 *>(zs + 2) = make_double2(zt[2], zt[3]);
+                *reinterpret_cast<double2 *>(ws) = make_double2(dl[0], dl[1]); *reinterpret_cast<double2 *>(ws + 2) = make_double2(dl[2], dl[3]);
+              }
+            } else {
+              if (lane == 0 && gsn[col] == 1.0) meta[col] = mt[k] | 512u;
+              mbar_wait(mbar + col, parity);
+              if (own) {
+                const double2 z01 = *reinterpret_cast<const double2 *>(js), z23 = *reinterpret_cast<const double2 *>(js + 2);
+                const double2 a01 = *reinterpret_cast<const double2 *>(ws), a23 = *reinterpret_cast<const double2 *>(ws + 2);
+                const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
+                *reinterpret_cast<double2 *>(zs) = make_double2(a01.x - b01.x, a01.y - b01.y);
+                *reinterpret_cast<double2 *>(zs + 2) = make_double2(a23.x - b23.x, a23.y - b23.y);
+                *reinterpret_cast<double2 *>(ws) = z01; *reinterpret_cast<double2 *>(ws + 2) = z23;
+              }
+            }
+          } else if (warp + GW_WARPS * k < nbc && own) {
+            // column of a chain slot past the end of the shard: keep its product finite
+            double *wz = Wc + (size_t)(warp + GW_WARPS * k) * ld + i0;
+            *reinterpret_cast<double2 *>(wz) = make_double2(0.0, 0.0); *reinterpret_cast<double2 *>(wz + 2) = make_double2(0.0, 0.0);
+          }
         }
       }
       if (do_refresh && warp < TC && own) {   // refresh columns: x (zero for empty chain slots)
@@ -377,71 +406,69 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
         const double2 a = *reinterpret_cast<const double2 *>(Ys + warp * ld + i0), b = *reinterpret_cast<const double2 *>(Ys + warp * ld + i0 + 2);
         y0[0] = a.x; y0[1] = a.y; y0[2] = b.x; y0[3] = b.y;
       }
-      // dx.(invC dx) of the columns (state independent; unused for snooker columns)
-      {
-        double sd[GW_MAXNB];
-#pragma unroll
-        for (int itb = 0; itb < GW_MAXNB; ++itb) {
-          double part = 0.0;
-          if (itb < nb && own) {
-            const int col = itb * TC + warp;
-            const double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
-            const double2 j01 = *reinterpret_cast<const double2 *>(js), j23 = *reinterpret_cast<const double2 *>(js + 2);
-            const double2 z01 = *reinterpret_cast<const double2 *>(zs), z23 = *reinterpret_cast<const double2 *>(zs + 2);
-            const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
-            part = fma(j01.x + z01.x, w01.x, part); part = fma(j01.y + z01.y, w01.y, part);
-            part = fma(j23.x + z23.x, w23.x, part); part = fma(j23.y + z23.y, w23.y, part);
-          }
-          sd[itb] = part;
+      double ntn_last = nan_to_num(1.0 * last_like + last_prior);
+      // column data of the iteration about to run (loaded one iteration ahead)
+      double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0};
+      uint32_t mt = 0;
+      double lu = 0.0, gsnk = 0.0, sd = 0.0;
+      auto load_col = [&](int itb, double (&aa)[4], double (&bb)[4], double (&ww)[4], uint32_t &m, double &l, double &g) {
+        const int col = itb * TC + warp;
+        if (own) {
+          const double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
+          const double2 j01 = *reinterpret_cast<const double2 *>(js), j23 = *reinterpret_cast<const double2 *>(js + 2);
+          const double2 z01 = *reinterpret_cast<const double2 *>(zs), z23 = *reinterpret_cast<const double2 *>(zs + 2);
+          const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
+          aa[0] = j01.x; aa[1] = j01.y; aa[2] = j23.x; aa[3] = j23.y;
+          bb[0] = z01.x; bb[1] = z01.y; bb[2] = z23.x; bb[3] = z23.y;
+          ww[0] = w01.x; ww[1] = w01.y; ww[2] = w23.x; ww[3] = w23.y;
         }
+        m = meta[col]; l = logu[col]; g = gsn[col];
+      };
+      load_col(0, a, b, w, mt, lu, gsnk);
+      {   // dx.(invC dx) of the first column; later ones ride along with the previous iteration's reduction
+        double part = 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int itb = 0; itb < GW_MAXNB; ++itb) sd[itb] += __shfl_xor_sync(0xffffffffu, sd[itb], o);
-        if (lane == 0) {
-#pragma unroll
-          for (int itb = 0; itb < GW_MAXNB; ++itb) if (itb < nb) sdot[itb * TC + warp] = sd[itb];
-        }
-        __syncwarp();
+        for (int j = 0; j < 4; ++j) part = fma(a[j] + b[j], w[j], part);
+        sd = gsum<32>(part, 0xffffffffu);
       }
-      GW_STAMP();   // c0: state loaded, sdot done
+      GW_STAMP();   // c0: state loaded
       double *trow_ptr = P.tr.trace + ((size_t)c_local * P.tr.trace_iters + (P.tr.trace_offset + done)) * ld + i0;
       double *lrow_ptr = P.tr.trace_logp + (size_t)c_local * P.tr.trace_iters + (P.tr.trace_offset + done);
       uint32_t *drow_ptr = P.tr.decisions ? P.tr.decisions + (size_t)c_local * P.tr.trace_iters + (P.tr.trace_offset + done) : nullptr;
 #pragma unroll 1
       for (int itb = 0; itb < nb; ++itb) {
-        const int col = itb * TC + warp;
-        const double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
-        double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0};
-        if (own) {
-          const double2 j01 = *reinterpret_cast<const double2 *>(js), j23 = *reinterpret_cast<const double2 *>(js + 2);
-          const double2 z01 = *reinterpret_cast<const double2 *>(zs), z23 = *reinterpret_cast<const double2 *>(zs + 2);
-          const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
-          a[0] = j01.x; a[1] = j01.y; a[2] = j23.x; a[3] = j23.y;
-          b[0] = z01.x; b[1] = z01.y; b[2] = z23.x; b[3] = z23.y;
-          w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y;
+        // next column (state independent): loads + its dx.(invC dx) partial
+        double an[4] = {0, 0, 0, 0}, bn[4] = {0, 0, 0, 0}, wnx[4] = {0, 0, 0, 0};
+        uint32_t mtn = 0;
+        double lun = 0.0, gn = 0.0, sdp = 0.0;
+        if (itb + 1 < nb) {
+          load_col(itb + 1, an, bn, wnx, mtn, lun, gn);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sdp = fma(an[j] + bn[j], wnx[j], sdp);
         }
-        const uint32_t mt = meta[col];
         const int run_snooker = (mt >> 8) & 1;
-        const double lu = logu[col];
-        const double last_logp = 1.0 * last_like + last_prior;
-        double prop[4], wn[4], mr, Qn;
+        double prop[4], wn[4], mr, Qn, q_like;
         if (!run_snooker) {
           // prop = q0 + e*gamma*diff + zeta (Dream.py:717); Q(prop) = Q + 2 dx.y + dx.(invC dx)
-          double part = 0.0;
+          double dl[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             prop[j] = x0[j] + a[j] + b[j];
             wn[j] = w[j];
-            part = fma(prop[j] - x0[j], y0[j], part);
+            dl[j] = prop[j] - x0[j];
           }
-          const double dot = gsum<32>(part, 0xffffffffu);
-          Qn = (Q0 + 2.0 * dot) + sdot[col];
-          const double q_logp = 1.0 * (logF - .5 * Qn) + 0.0;
-          mr = nan_to_num(q_logp) - nan_to_num(last_logp);                               // Dream.py:334
+          double part = fma(dl[1], y0[1], dl[0] * y0[0]) + fma(dl[3], y0[3], dl[2] * y0[2]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            part += __shfl_xor_sync(0xffffffffu, part, o);
+            sdp += __shfl_xor_sync(0xffffffffu, sdp, o);
+          }
+          Qn = (Q0 + (part + part)) + sd;
+          q_like = logF - .5 * Qn;
+          mr = nan_to_num(q_like) - ntn_last;                                            // Dream.py:334
         } else {
           // snooker_update, Dream.py:827-835 (single-point form); a = z, b = z1 - z2, w = invC z
-          const double gamma = gsn[col];
+          const double gamma = gsnk;
           double v[4], t[4];
           double D = 0.0, S = 0.0;
 #pragma unroll
@@ -450,7 +477,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
             D = fma(v[j], v[j], D);
             t[j] = b[j] * v[j];
           }
-          D = gsum<32>(D, 0xffffffffu);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            D += __shfl_xor_sync(0xffffffffu, D, o);
+            sdp += __shfl_xor_sync(0xffffffffu, sdp, o);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) S += (D != 0) ? t[j] / D : 0.0;
           const double sc = nan_to_num(gsum<32>(S, 0xffffffffu));
@@ -479,23 +510,21 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
           const double n0 = sqrt(D);
           const double cur = (n0 != 0 ? log(n0) : 0.0) * (d - 1);
           Qn = (Q0 + 2.0 * p1) + p2;
-          const double q_logp = 1.0 * (logF - .5 * Qn) + 0.0;
-          mr = nan_to_num((q_logp + snk_logp) - (last_logp + cur));                      // Dream.py:326-332
+          q_like = logF - .5 * Qn;
+          mr = nan_to_num((q_like + snk_logp) - ((1.0 * last_like + last_prior) + cur));   // Dream.py:326-332
         }
-        bool accepted = false;
-        if (isfinite(mr)) accepted = lu < mr;                                            // metrop_select, Dream.py:980-998
-        int changed = 0;
-        if (accepted) {
+        int anydiff = 0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) changed |= (prop[j] != x0[j]);
-        }
-        changed = __any_sync(0xffffffffu, changed);
+        for (int j = 0; j < 4; ++j) anydiff |= (prop[j] != x0[j]);
+        const bool accepted = isfinite(mr) && lu < mr;                                   // metrop_select, Dream.py:980-998
+        const int changed = accepted && __any_sync(0xffffffffu, anydiff);
         if (changed) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) { x0[j] = prop[j]; y0[j] = y0[j] + wn[j]; }
           Q0 = Qn;
           last_prior = 0.0;
-          last_like = logF - .5 * Qn;
+          last_like = q_like;
+          ntn_last = nan_to_num(q_like);
         }
         if (own) {
           *reinterpret_cast<double2 *>(trow_ptr) = make_double2(x0[0], x0[1]);
@@ -512,6 +541,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
             *drow_ptr = pack_decision(changed, run_snooker, mt & 15, (mt >> 4) & 15, 1, 0, (mt >> 9) & 1, accepted);
         }
         trow_ptr += ld; lrow_ptr += 1; if (drow_ptr) drow_ptr += 1;
+        // rotate in the next column
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[j] = an[j]; b[j] = bn[j]; w[j] = wnx[j]; }
+        mt = mtn; lu = lun; gsnk = gn; sd = sdp;
         GW_STAMP();   // c: iteration done
       }
       // park the chain state for the next batch / the epilogue

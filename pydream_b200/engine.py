@@ -81,7 +81,7 @@ class DreamEngine:
                  nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
                  history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
                  cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True,
-                 generic_kernel=False, window_kernel=True):
+                 generic_kernel=False, window_kernel=True, reserve_iters=0):
         if not torch.cuda.is_available():
             raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _cabi.load()
@@ -107,7 +107,8 @@ class DreamEngine:
         self.iter = 0
         self._hist_host = history
         self.Z = None
-        self._ensure_capacity(self.nseed)
+        # the archive is sized once for `reserve_iters` iterations (it grows on demand beyond that)
+        self._ensure_capacity(self.nseed + appends_in(0, int(reserve_iters), self.thin) * N)
         starts = np.asarray(starts, dtype=np.float64).reshape(N, d)
         Xh = np.zeros((self.Nl, self.ld))
         Xh[:, :d] = starts[self.c0:self.c0 + self.Nl]
@@ -168,7 +169,8 @@ class DreamEngine:
     def _ensure_capacity(self, rows):
         if self.Z is not None and self.Z.shape[0] >= rows:
             return
-        Z = torch.zeros((rows, self.ld), dtype=torch.float64, device=self.device)
+        # rows past the current size are written (record_history) before they can be sampled: no zero-fill
+        Z = torch.empty((rows, self.ld), dtype=torch.float64, device=self.device)
         if self.Z is None:
             # seed rows: one host->device copy of the caller's array (asynchronous when it lives in pinned memory),
             # padded to the row stride on the device
@@ -178,9 +180,10 @@ class DreamEngine:
                 Z[:self.nseed] = hd
             else:
                 Z[:self.nseed, :self.d] = hd
+                Z[:self.nseed, self.d:] = 0
             self._hist_host = None
         else:
-            Z[:self.Z.shape[0]] = self.Z
+            Z[:self.archive_rows] = self.Z[:self.archive_rows]
         self.Z = Z
         if hasattr(self, 'st'):
             self._state()
