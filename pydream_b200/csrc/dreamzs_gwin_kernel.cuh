@@ -9,16 +9,21 @@
 // state x -- is a function of the Philox counters and of the archive, which is constant inside a
 // launch.  And with y = invC x and Q = x.y carried per chain, the quadratic form of a proposal is
 //     Q(x + dx) = Q + 2 dx.y + dx.(invC dx),
-// where w = invC dx does not depend on x either.  So a launch works in batches of NB iterations
-// of the CTA's TC chains (NB*TC "columns"):
-//   G  (warp per column)  all draws of the column in one lane-parallel Philox pass; archive rows
-//                         TMA-staged straight into the shared-memory slots that will hold the
-//                         jump (UBLKCP + mbarrier complete_tx); dx, zeta and the crossover mask
-//   M  (warp per tile)    W = invC * [dx columns | snooker z columns | x columns on refresh]:
-//                         register-tiled fp64 products, 4 rows x TC columns per thread, K split
-//                         3-fold over warps, one (column group, K range) per warp
+// where w = invC dx does not depend on x either.  So a launch works in batches of NB iterations;
+// a (chain, iteration) pair is a "column":
+//   G  (warp per column)  all scalar draws of a warp's columns in ONE lane-parallel Philox pass;
+//                         archive rows TMA-staged straight into the shared-memory slots that will
+//                         hold the jump (UBLKCP + mbarrier complete_tx); dx, zeta, crossover mask
+//   M  (warp per tile)    W = invC * [dx columns | snooker z columns | x column on refresh]:
+//                         register-tiled fp64 products, tile = one chain's columns x 4 rows per
+//                         lane, K split 2-fold over warps
 //   C  (warp per chain)   the Markov chain itself: per iteration 2 adds, one 4-wide dot product and
 //                         ONE warp reduction, the Metropolis test, trace write, archive append
+// The three phases stress different units (G: integer pipe + fp64 transcendentals, M: fp64 FMA +
+// shared memory, C: latency), so the CTA is split into GW_GROUPS independent warp groups, each
+// owning a share of the CTA's chains and running G -> M -> C on its own named barrier; the groups
+// drift apart and one group's M overlaps the other's G or C.  The precision matrix (80 KB at
+// d=100) is shared by the groups.
 // The snooker move is linear in the state as well: dx = c (x - z), invC dx = c (y - invC z), so
 // its column of M is invC z.  y and Q are refreshed from x every DREAMZS_GAUSS_REFRESH_WINDOWS
 // windows so rounding drift stays orders of magnitude below the 1e-12 parity tolerance.
@@ -31,20 +36,30 @@
 namespace dreamzs {
 
 constexpr int GW_THREADS = 512;
-constexpr int GW_WARPS = GW_THREADS / 32;
-constexpr int GW_KS = 3;       // K split of the products; fixed: the summation order is part of the result
-constexpr int GW_MAXNB = 5;    // iterations per batch: GW_MAXNB * GW_KS tiles <= GW_WARPS
-constexpr int GW_MAXCOLW = 3;  // columns a warp generates per batch: ceil(GW_MAXNB * 8 / GW_WARPS)
+constexpr int GW_GROUPS = 2;                               // independent warp groups per CTA
+constexpr int GW_GWARPS = GW_THREADS / 32 / GW_GROUPS;     // warps per group
+constexpr int GW_GTHREADS = GW_GWARPS * 32;
+constexpr int GW_KS = 2;       // K split of the products; fixed: the summation order is part of the result
+constexpr int GW_MAXNB = 5;    // iterations per batch
+constexpr int GW_MAXCOLW = 3;  // columns a warp generates per batch (3 x 10 lanes of scalar draws)
+
+__host__ __device__ inline int gwin_group_chains(int TC, int g) { return (TC + GW_GROUPS - 1 - g) / GW_GROUPS; }
+__host__ __device__ inline int gwin_group_first(int TC, int g) {
+  int b = 0;
+  for (int i = 0; i < g; ++i) b += gwin_group_chains(TC, i);
+  return b;
+}
 
 struct GwinLayout {
-  int d2, ncol;
-  size_t oAt, oWc, oJc, oZc, oXs, oYs, oGam, oSdot, oLogu, oGsn, oProbs, oMbar, oMeta, bytes;
+  int d2, ncol, gcap;
+  size_t oAt, oWc, oJc, oZc, oXs, oYs, oGam, oLogu, oGsn, oProbs, oMbar, oMeta, bytes;
 };
 
 __host__ __device__ inline GwinLayout gwin_layout(int d, int ld, int TC, int NB, int ngamma) {
   GwinLayout L;
   L.d2 = (d + 1) & ~1;
-  L.ncol = NB * TC;
+  L.gcap = gwin_group_chains(TC, 0) * NB;            // column slots per group (chain-major: chain * NB + iteration)
+  L.ncol = L.gcap * GW_GROUPS;
   size_t o = 0;
   L.oAt = o;    o += (size_t)L.d2 * ld;              // precision matrix, transposed, row stride ld
   L.oWc = o;    o += (size_t)(L.ncol + TC) * ld;     // dx / z columns -> invC * column; + TC refresh columns
@@ -53,7 +68,6 @@ __host__ __device__ inline GwinLayout gwin_layout(int d, int ld, int TC, int NB,
   L.oXs = o;    o += (size_t)TC * ld;                // chain states between the C phases
   L.oYs = o;    o += (size_t)TC * ld;
   L.oGam = o;   o += ((size_t)ngamma * d + 1) & ~(size_t)1;
-  L.oSdot = o;  o += L.ncol;
   L.oLogu = o;  o += L.ncol;
   L.oGsn = o;   o += L.ncol;
   L.oProbs = o; o += 32 + 4 * TC;
@@ -61,6 +75,18 @@ __host__ __device__ inline GwinLayout gwin_layout(int d, int ld, int TC, int NB,
   L.oMeta = o;  o += (L.ncol + 1) / 2;
   L.bytes = o * sizeof(double);
   return L;
+}
+
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void group_sync(int gid) {
+  asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(GW_GTHREADS) : "memory");
 }
 
 template <int TC>
@@ -71,11 +97,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
   const int d2 = L.d2, ncol = L.ncol;
   double *At = smem + L.oAt, *Wc = smem + L.oWc, *Jc = smem + L.oJc, *Zc = smem + L.oZc;
   double *Xs = smem + L.oXs, *Ys = smem + L.oYs, *gam = smem + L.oGam;
-  double *sdot = smem + L.oSdot, *logu = smem + L.oLogu, *gsn = smem + L.oGsn;
+  double *logu = smem + L.oLogu, *gsn = smem + L.oGsn;
   double *probs = smem + L.oProbs, *cst = probs + 32;   // cst: per chain [Q, last_prior, last_like, -]
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L.oMbar);   // [ncol] columns, [ncol] precision matrix
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L.oMbar);   // [0, ncol) columns, [ncol] precision matrix
   uint32_t *meta = reinterpret_cast<uint32_t *>(smem + L.oMeta);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = warp / GW_GWARPS, gw = warp - gid * GW_GWARPS;    // warp group, warp within the group
   const double logF = P.st.target_table[0];
   int dbg_n = 0;
 #define GW_STAMP() do { if (P.dbg && blockIdx.x == 0 && tid == 0) P.dbg[dbg_n] = clock64(); ++dbg_n; } while (0)
@@ -88,7 +115,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
   const uint32_t s0 = P.cfg.snooker != 0 ? 1u : 0u;   // multinomial call number of the CR draw
   const uint32_t k0 = (uint32_t)P.cfg.seed, k1 = (uint32_t)(P.cfg.seed >> 32);
   const int cta_chain0 = blockIdx.x * TC;
-  const int nch = min(TC, P.cfg.nchains_local - cta_chain0);   // chains of this CTA
+  const int nch_cta = min(TC, P.cfg.nchains_local - cta_chain0);   // chains of this CTA
+  const int gfirst = gwin_group_first(TC, gid);                     // first chain slot of this group
+  const int gch = max(0, min(gwin_group_chains(TC, gid), nch_cta - gfirst));   // chains of this group
+  const int gbase = gid * L.gcap;                                   // first column slot of this group
 
   // ---- prologue: one TMA bulk copy brings the precision matrix; chain states -> shared memory
   if (tid < ncol + 1) mbar_init(mbar + tid, 1);
@@ -105,7 +135,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
     gam[i] = P.st.gamma_table[(size_t)lv * P.cfg.nDEpairs * d + (i - lv * d)];
   }
   if ((d & 1) && tid < ld) At[(size_t)d * ld + tid] = 0.0;     // padding row of the j-pair loop
-  if (warp < nch) {
+  if (warp < nch_cta) {
     const int c_local = cta_chain0 + warp;
     if (own) {
       const double *xrow = P.st.X + (size_t)c_local * ld + i0;
@@ -138,262 +168,261 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
   int done = 0;
   for (int batch = 0; done < P.niter; ++batch) {
     const int nb = min(NB, P.niter - done);
-    const int nbc = nb * TC;                               // columns of this batch: col = iteration * TC + chain
     const bool do_refresh = P.gw_refresh && batch == 0;
     const uint32_t parity = (uint32_t)(batch & 1);
     // ================================================================ G: generation (warp per column)
-    // A warp owns the columns warp, warp+16, warp+32 of the batch and works on them in lock-step (straight-line
-    // code over the three: the long dependent chains of Philox / log / Box-Muller interleave).
+    // group-local column index cl = chain * NB + iteration; the warp owns cl = gw, gw + 8, gw + 16
     {
-      int colk[GW_MAXCOLW];
-      bool valid[GW_MAXCOLW];
-      uint32_t iterk[GW_MAXCOLW], chk[GW_MAXCOLW];
-#pragma unroll
-      for (int k = 0; k < GW_MAXCOLW; ++k) {
-        const int col = warp + GW_WARPS * k;
-        const int itb = col / TC, ch = col - itb * TC;
-        valid[k] = col < nbc && ch < nch;
-        colk[k] = valid[k] ? col : 0;
-        iterk[k] = (uint32_t)(P.iter_begin + done + (valid[k] ? itb : 0));
-        chk[k] = (uint32_t)(P.cfg.chain_begin + cta_chain0 + (valid[k] ? ch : 0));
-      }
-      // ---- S: scalar draws and archive rows, one Philox block per lane:
-      //      lanes 0-5: snooker, CR, gamma level, gamma unity (Dream.py:542-599, 615), first two
-      //      np.random.uniform() (snooker gamma :618 / Metropolis :993); lanes 8-10: random.sample calls 0-2
+      // ---- S: scalar draws and archive rows of the warp's columns in one pass, 10 lanes per column:
+      //      0-5: snooker, CR, gamma level, gamma unity (Dream.py:542-599, 615), first two np.random.uniform()
+      //      (snooker gamma :618 / Metropolis :993); 6-8: random.sample calls 0-2 (sample_from_history, :646-668)
+      const int sk = min(lane / 10, GW_MAXCOLW - 1), kind = lane - 10 * (lane / 10);
+      int snk_k[GW_MAXCOLW];
       {
+        const int cl = gw + GW_GWARPS * sk;
+        const int ch = cl / NB, itb = cl - ch * NB;
+        const bool ok = lane < 10 * GW_MAXCOLW && ch < gch && itb < nb;
+        const uint32_t iter = (uint32_t)(P.iter_begin + done + (ok ? itb : 0));
+        const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + gfirst + (ok ? ch : 0));
         uint32_t call = 0, st = ST_MULTINOMIAL;
         const double *pp = probs + 24;
         int n = 2;
-        if (lane == 1) { call = s0; pp = probs; n = P.cfg.nCR; }
-        else if (lane == 2) { call = s0 + 1; pp = probs + 16; n = P.cfg.ngamma; }
-        else if (lane == 3) { call = s0 + 2; pp = probs + 26; }
-        else if (lane == 4) { st = ST_UNIFORM_SCAL; }
-        else if (lane == 5) { call = 1; st = ST_UNIFORM_SCAL; }
-        else if (lane >= 8) { call = (uint32_t)(lane - 8) & 3u; st = ST_SAMPLE; }
-        const int nmax = max(2, max(P.cfg.nCR, P.cfg.ngamma));
-        uint4 w[GW_MAXCOLW];
-        double u[GW_MAXCOLW], acc[GW_MAXCOLW], lg[GW_MAXCOLW];
-        int idx[GW_MAXCOLW];
+        if (kind == 1) { call = s0; pp = probs; n = P.cfg.nCR; }
+        else if (kind == 2) { call = s0 + 1; pp = probs + 16; n = P.cfg.ngamma; }
+        else if (kind == 3) { call = s0 + 2; pp = probs + 26; }
+        else if (kind == 4) { st = ST_UNIFORM_SCAL; }
+        else if (kind == 5) { call = 1; st = ST_UNIFORM_SCAL; }
+        else if (kind >= 6) { call = (uint32_t)(kind - 6); st = ST_SAMPLE; }
+        const uint4 w = philox4x32(0u, (call << 3) | st, iter, c_global, k0, k1);
+        const double u = u53_of(w.x, w.y);
+        double acc = 0.0;
+        int idx = n - 1;
+        bool found = false;
+        for (int j = 0; j < n; ++j) {
+          acc = acc + pp[j];
+          if (!found && u < acc) { idx = j; found = true; }
+        }
+        const double lg = log(u);
+        int64_t r0 = (int64_t)(((uint64_t)w.x * (uint64_t)M) >> 32);
+        int64_t r1 = (int64_t)(((uint64_t)w.y * (uint64_t)(M - 1)) >> 32);
+        if (r1 >= r0) r1 += 1;
+        // column decisions -> every lane of the column's 10
+        const int base = 10 * sk;
+        const int snk = (s0 != 0u) && __shfl_sync(0xffffffffu, idx, base) == 0;
+        const int cr_s = __shfl_sync(0xffffffffu, idx, base + 1), lvl_s = __shfl_sync(0xffffffffu, idx, base + 2);
+        const int unity_s = __shfl_sync(0xffffffffu, idx, base + 3);
 #pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) w[k] = philox4x32(0u, (call << 3) | st, iterk[k], chk[k], k0, k1);
-#pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) { u[k] = u53_of(w[k].x, w[k].y); acc[k] = 0.0; idx[k] = n - 1; }
-        unsigned found = 0;
-        for (int j = 0; j < nmax; ++j) {
-          const double pj = j < n ? pp[j] : 0.0;
-#pragma unroll
-          for (int k = 0; k < GW_MAXCOLW; ++k) {
-            acc[k] = acc[k] + pj;
-            if (j < n && !((found >> k) & 1u) && u[k] < acc[k]) { idx[k] = j; found |= 1u << k; }
+        for (int k = 0; k < GW_MAXCOLW; ++k) snk_k[k] = __shfl_sync(0xffffffffu, snk, 10 * k);
+        const int col = gbase + cl;
+        if (ok) {
+          // meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set in V), 10 "not unity"
+          if (kind == 0) meta[col] = (uint32_t)cr_s | ((uint32_t)lvl_s << 4) | (snk ? 256u : 0u) | (unity_s != 0 ? 1024u : 0u);
+          if (kind == (snk ? 5 : 4)) logu[col] = lg;                               // Metropolis uniform: 2nd draw after a snooker gamma
+          if (kind == 4) gsn[col] = 1.2 + (2.2 - 1.2) * u;                         // snooker gamma, Dream.py:618
+          if (kind == 6) {
+            fence_proxy_async();   // earlier generic-proxy accesses of the slots are ordered before the async writes
+            mbar_expect_tx(mbar + col, row_bytes * (snk ? 3u : 2u));
           }
         }
-#pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) lg[k] = log(u[k]);
-        GW_STAMP();   // s1: philox, multinomial, log
-#pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) {
-          // decisions of the column -> meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set
-          // in V), 10 gamma-unity draw says "not unity"
-          const unsigned bal_snk = __ballot_sync(0xffffffffu, idx[k] == 0);
-          const int snk = (s0 != 0u) && (bal_snk & 1u);
-          const int cr_s = __shfl_sync(0xffffffffu, idx[k], 1), lvl_s = __shfl_sync(0xffffffffu, idx[k], 2);
-          const int unity_s = __shfl_sync(0xffffffffu, idx[k], 3);
-          // archive rows (sample_from_history, Dream.py:646-668), TMA-staged into the column's slots:
-          //   DE      z_r1 -> J slot, z_r2 -> zeta slot;   snooker  z -> J slot, z1 -> W slot, z2 -> zeta slot
-          int64_t r0 = (int64_t)(((uint64_t)w[k].x * (uint64_t)M) >> 32);
-          int64_t r1 = (int64_t)(((uint64_t)w[k].y * (uint64_t)(M - 1)) >> 32);
-          if (r1 >= r0) r1 += 1;
-          if (valid[k]) {
-            const int col = colk[k];
-            if (lane == 0) meta[col] = (uint32_t)cr_s | ((uint32_t)lvl_s << 4) | (snk ? 256u : 0u) | (unity_s != 0 ? 1024u : 0u);
-            if (lane == (snk ? 5 : 4)) logu[col] = lg[k];                            // Metropolis uniform: 2nd draw after a snooker gamma
-            if (lane == 4) gsn[col] = 1.2 + (2.2 - 1.2) * u[k];                      // snooker gamma, Dream.py:618
-            if (lane == 8) {
-              fence_proxy_async();   // earlier generic-proxy accesses of the slots are ordered before the async writes
-              mbar_expect_tx(mbar + col, row_bytes * (snk ? 3u : 2u));
+        __syncwarp();
+        if (ok) {
+          // DE: z_r1 -> J slot, z_r2 -> zeta slot;   snooker: z -> J slot, z1 -> W slot, z2 -> zeta slot
+          double *js = Jc + (size_t)col * ld, *zs = Zc + (size_t)col * ld, *ws = Wc + (size_t)col * ld;
+          if (!snk) {
+            if (kind == 6) {
+              tma_load_row(js, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
+              tma_load_row(zs, P.st.Z + (size_t)r1 * ld, row_bytes, mbar + col);
             }
-            __syncwarp();
-            double *js = Jc + (size_t)col * ld, *zs = Zc + (size_t)col * ld, *ws = Wc + (size_t)col * ld;
-            if (!snk) {
-              if (lane == 8) {
-                tma_load_row(js, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
-                tma_load_row(zs, P.st.Z + (size_t)r1 * ld, row_bytes, mbar + col);
-              }
-            } else if (lane >= 8 && lane <= 10) {
-              fence_proxy_async();
-              tma_load_row(lane == 8 ? js : lane == 9 ? ws : zs, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
-            }
+          } else if (kind >= 6 && kind <= 8) {
+            fence_proxy_async();
+            tma_load_row(kind == 6 ? js : kind == 7 ? ws : zs, P.st.Z + (size_t)r0 * ld, row_bytes, mbar + col);
           }
         }
         __syncwarp();
       }
       GW_STAMP();   // +0: rows requested (warp 0)
-      // ---- V: the columns (generate_proposal_points DE branch, Dream.py:688-726; snooker rows, :808-810).
-      //      The DE variates are drawn for every column (a snooker column, 1 in 10, discards them).
-      {
-        double zeta[GW_MAXCOLW][4], e[GW_MAXCOLW][4];
-        unsigned reset[GW_MAXCOLW];
-        int dprime[GW_MAXCOLW];
-        uint32_t mt[GW_MAXCOLW];
-        const bool act = own && i0 < d;
+      // ---- V: the columns (generate_proposal_points DE branch, Dream.py:688-726; snooker rows, :808-810)
+#pragma unroll 1
+      for (int k = 0; k < GW_MAXCOLW; ++k) {
+        const int cl = gw + GW_GWARPS * k;
+        const int ch = cl / NB, itb = cl - ch * NB;
+        if (ch >= gch || itb >= nb) continue;
+        const int col = gbase + cl;
+        const uint32_t iter = (uint32_t)(P.iter_begin + done + itb);
+        const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + gfirst + ch);
+        const uint32_t mt = meta[col];
+        const int snk = (mt >> 8) & 1, cr_idx = mt & 15, lvl_idx = (mt >> 4) & 15;
+        double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
+        if (!snk) {
+          double zeta[4] = {0, 0, 0, 0}, e[4] = {1, 1, 1, 1};
+          unsigned reset = 15u;
+          int dprime = 0;
+          if (own && i0 < d) {
+            double nz[4];
+            normal4(philox4x32((uint32_t)lane, (0u << 3) | ST_NORMAL, iter, c_global, k0, k1), nz);
+            const uint4 we = philox4x32((uint32_t)lane, (0u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
+            const uint4 wu = philox4x32((uint32_t)lane, (1u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
+            const uint32_t wev[4] = {we.x, we.y, we.z, we.w}, wuv[4] = {wu.x, wu.y, wu.z, wu.w};
+            // U = w 2^-32 exactly, so U < CR <=> w < ceil(CR 2^32) and U > CR <=> w > floor(CR 2^32)
+            const double CRs = ((double)(cr_idx + 1) / (double)P.cfg.nCR) * 4294967296.0;
+            const uint64_t t_lt = (uint64_t)ceil(CRs), t_gt = (uint64_t)floor(CRs);
+            reset = 0;
 #pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) mt[k] = meta[colk[k]];
-        uint4 wn[GW_MAXCOLW], we[GW_MAXCOLW], wu[GW_MAXCOLW];
-#pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) {
-          wn[k] = philox4x32((uint32_t)lane, (0u << 3) | ST_NORMAL, iterk[k], chk[k], k0, k1);
-          we[k] = philox4x32((uint32_t)lane, (0u << 3) | ST_UNIFORM_VEC, iterk[k], chk[k], k0, k1);
-          wu[k] = philox4x32((uint32_t)lane, (1u << 3) | ST_UNIFORM_VEC, iterk[k], chk[k], k0, k1);
-        }
-#pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) {
-          double nz[4];
-          normal4(wn[k], nz);
-          const uint32_t wev[4] = {we[k].x, we[k].y, we[k].z, we[k].w}, wuv[4] = {wu[k].x, wu[k].y, wu[k].z, wu[k].w};
-          // U = w 2^-32 exactly, so U < CR <=> w < ceil(CR 2^32) and U > CR <=> w > floor(CR 2^32)
-          const double CRs = ((double)((mt[k] & 15u) + 1u) / (double)P.cfg.nCR) * 4294967296.0;
-          const uint64_t t_lt = (uint64_t)ceil(CRs), t_gt = (uint64_t)floor(CRs);
-          reset[k] = 0; dprime[k] = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            zeta[k][j] = 0.0 + P.cfg.zeta * nz[j];
-            e[k][j] = (-P.cfg.lamb + (P.cfg.lamb - (-P.cfg.lamb)) * u32_of(wev[j])) + 1;
-            const bool in = act && i0 + j < d;
-            dprime[k] += (in && (uint64_t)wuv[j] < t_lt) ? 1 : 0;
-            if (!in || (uint64_t)wuv[j] > t_gt) reset[k] |= 1u << j;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) dprime[k] = __reduce_add_sync(0xffffffffu, dprime[k]);
-        GW_STAMP();   // v1: variates
-#pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) {
-          const int col = colk[k];
-          const int snk = (mt[k] >> 8) & 1, lvl_idx = (mt[k] >> 4) & 15;
-          double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
-          if (valid[k]) {
-            if (!snk) {
-              double gamma = 1.0;
-              if (mt[k] & 1024u) gamma = gam[lvl_idx * d + (dprime[k] >= 1 ? dprime[k] - 1 : d - 1)];
-              if (lane == 0 && gamma == 1.0) meta[col] = mt[k] | 512u;
-              mbar_wait(mbar + col, parity);
-              if (own) {
-                const double2 a01 = *reinterpret_cast<const double2 *>(js), a23 = *reinterpret_cast<const double2 *>(js + 2);
-                const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
-                const double diff[4] = {a01.x - b01.x, a01.y - b01.y, a23.x - b23.x, a23.y - b23.y};
-                double J[4], zt[4], dl[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const bool keep = !((reset[k] >> j) & 1u);
-                  J[j] = keep ? (e[k][j] * gamma) * diff[j] : 0.0;
-                  zt[j] = keep ? zeta[k][j] : 0.0;
-                  dl[j] = J[j] + zt[j];
-                }
-                *reinterpret_cast<double2 *>(js) = make_double2(J[0], J[1]); *reinterpret_cast<double2 *>(js + 2) = make_double2(J[2], J[3]);
-                *reinterpret_cast<double2 *>(zs) = make_double2(zt[0], zt[1]); *reinterpret_cast<double2 *>(zs + 2) = make_double2(zt[2], zt[3]);
-                *reinterpret_cast<double2 *>(ws) = make_double2(dl[0], dl[1]); *reinterpret_cast<double2 *>(ws + 2) = make_double2(dl[2], dl[3]);
-              }
-            } else {
-              if (lane == 0 && gsn[col] == 1.0) meta[col] = mt[k] | 512u;
-              mbar_wait(mbar + col, parity);
-              if (own) {
-                const double2 z01 = *reinterpret_cast<const double2 *>(js), z23 = *reinterpret_cast<const double2 *>(js + 2);
-                const double2 a01 = *reinterpret_cast<const double2 *>(ws), a23 = *reinterpret_cast<const double2 *>(ws + 2);
-                const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
-                *reinterpret_cast<double2 *>(zs) = make_double2(a01.x - b01.x, a01.y - b01.y);
-                *reinterpret_cast<double2 *>(zs + 2) = make_double2(a23.x - b23.x, a23.y - b23.y);
-                *reinterpret_cast<double2 *>(ws) = z01; *reinterpret_cast<double2 *>(ws + 2) = z23;
-              }
+            for (int j = 0; j < 4; ++j) {
+              zeta[j] = 0.0 + P.cfg.zeta * nz[j];
+              e[j] = (-P.cfg.lamb + (P.cfg.lamb - (-P.cfg.lamb)) * u32_of(wev[j])) + 1;
+              if (i0 + j < d) {
+                dprime += ((uint64_t)wuv[j] < t_lt);
+                if ((uint64_t)wuv[j] > t_gt) reset |= 1u << j;
+              } else reset |= 1u << j;
             }
-          } else if (warp + GW_WARPS * k < nbc && own) {
-            // column of a chain slot past the end of the shard: keep its product finite
-            double *wz = Wc + (size_t)(warp + GW_WARPS * k) * ld + i0;
-            *reinterpret_cast<double2 *>(wz) = make_double2(0.0, 0.0); *reinterpret_cast<double2 *>(wz + 2) = make_double2(0.0, 0.0);
+          }
+          dprime = __reduce_add_sync(0xffffffffu, dprime);
+          double gamma = 1.0;
+          if (mt & 1024u) gamma = gam[lvl_idx * d + (dprime >= 1 ? dprime - 1 : d - 1)];
+          if (lane == 0 && gamma == 1.0) meta[col] = mt | 512u;
+          mbar_wait(mbar + col, parity);
+          if (own) {
+            const double2 a01 = *reinterpret_cast<const double2 *>(js), a23 = *reinterpret_cast<const double2 *>(js + 2);
+            const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
+            const double diff[4] = {a01.x - b01.x, a01.y - b01.y, a23.x - b23.x, a23.y - b23.y};
+            double J[4], zt[4], dl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool keep = !((reset >> j) & 1u);
+              J[j] = keep ? (e[j] * gamma) * diff[j] : 0.0;
+              zt[j] = keep ? zeta[j] : 0.0;
+              dl[j] = J[j] + zt[j];
+            }
+            *reinterpret_cast<double2 *>(js) = make_double2(J[0], J[1]); *reinterpret_cast<double2 *>(js + 2) = make_double2(J[2], J[3]);
+            *reinterpret_cast<double2 *>(zs) = make_double2(zt[0], zt[1]); *reinterpret_cast<double2 *>(zs + 2) = make_double2(zt[2], zt[3]);
+            *reinterpret_cast<double2 *>(ws) = make_double2(dl[0], dl[1]); *reinterpret_cast<double2 *>(ws + 2) = make_double2(dl[2], dl[3]);
+          }
+        } else {
+          if (lane == 0 && gsn[col] == 1.0) meta[col] = mt | 512u;
+          mbar_wait(mbar + col, parity);
+          if (own) {
+            const double2 z01 = *reinterpret_cast<const double2 *>(js), z23 = *reinterpret_cast<const double2 *>(js + 2);
+            const double2 a01 = *reinterpret_cast<const double2 *>(ws), a23 = *reinterpret_cast<const double2 *>(ws + 2);
+            const double2 b01 = *reinterpret_cast<const double2 *>(zs), b23 = *reinterpret_cast<const double2 *>(zs + 2);
+            *reinterpret_cast<double2 *>(zs) = make_double2(a01.x - b01.x, a01.y - b01.y);
+            *reinterpret_cast<double2 *>(zs + 2) = make_double2(a23.x - b23.x, a23.y - b23.y);
+            *reinterpret_cast<double2 *>(ws) = z01; *reinterpret_cast<double2 *>(ws + 2) = z23;
           }
         }
       }
-      if (do_refresh && warp < TC && own) {   // refresh columns: x (zero for empty chain slots)
-        double *ws = Wc + (size_t)(ncol + warp) * ld + i0;
-        double2 a = make_double2(0.0, 0.0), b = a;
-        if (warp < nch) { a = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0); b = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0 + 2); }
-        *reinterpret_cast<double2 *>(ws) = a; *reinterpret_cast<double2 *>(ws + 2) = b;
+      (void)snk_k;
+      if (do_refresh && gw < gch && own) {   // refresh column of chain gw: x
+        double *ws = Wc + (size_t)(ncol + gfirst + gw) * ld + i0;
+        *reinterpret_cast<double2 *>(ws) = *reinterpret_cast<const double2 *>(Xs + (gfirst + gw) * ld + i0);
+        *reinterpret_cast<double2 *>(ws + 2) = *reinterpret_cast<const double2 *>(Xs + (gfirst + gw) * ld + i0 + 2);
       }
     }
     GW_STAMP();   // +1: columns of warp 0 generated
     if (batch == 0) mbar_wait(mbar + ncol, 0);   // precision matrix has landed
-    __syncthreads();
-    GW_STAMP();   // +2: all warps generated
+    group_sync(gid);
+    GW_STAMP();   // +2: the group's columns generated
     // ================================================================ M: W = invC * columns (warp per tile)
-    // tile = (column group of TC columns, K range); lane = row group: rows 2l, 2l+1, ld/2+2l, ld/2+2l+1
-    for (int pass = 0; pass < (do_refresh ? 2 : 1); ++pass) {
-      const int ncg = pass == 0 ? nb : 1;
-      const bool active = warp < ncg * GW_KS && lane < nq;
-      const int cgi = warp % ncg, ks = warp / ncg;
-      const int colbase = pass == 0 ? cgi * TC : ncol;
-      double acc[4][TC];
+    // tile = (chain of the group: its NB columns + its refresh column, K range); lane = row group:
+    // rows 2l, 2l+1, ld/2+2l, ld/2+2l+1.  Columns that do not exist in this batch (short last batch, no
+    // refresh) alias an existing one and are not written back.
+    {
+      const int tch = gw % gwin_group_chains(TC, 0), ks = gw / gwin_group_chains(TC, 0);
+      const bool active = tch < gch && ks < GW_KS && lane < nq;
+      const int ncc = nb + (do_refresh ? 1 : 0);
+      double acc[4][GW_MAXNB + 1];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int cc = 0; cc < TC; ++cc) acc[r][cc] = 0.0;
+        for (int cc = 0; cc <= GW_MAXNB; ++cc) acc[r][cc] = 0.0;
+      uint32_t xaddr[GW_MAXNB + 1];       // shared-window byte addresses of the tile's columns
+#pragma unroll
+      for (int cc = 0; cc <= GW_MAXNB; ++cc) {
+        int c = gbase + tch * NB + min(cc, nb - 1);                      // iteration cc of the chain
+        if (cc >= nb) c = do_refresh ? ncol + gfirst + tch : gbase + tch * NB;   // its refresh column / an alias
+        xaddr[cc] = smem_u32(Wc + (size_t)c * ld);
+      }
       if (active) {
         const int jb = min(d2, ks * jl), je = min(d2, jb + jl);
-        const double *ap = At + 2 * lane;
-        const double *xp = Wc + (size_t)colbase * ld;
-        const int hb = ld / 2;
+        const uint32_t hb = (uint32_t)ld * 4u;                           // ld/2 doubles in bytes
+        const uint32_t rowb = (uint32_t)ld * 8u;
+        uint32_t ap = smem_u32(At + 2 * lane) + (uint32_t)jb * rowb;
+        uint32_t joff = (uint32_t)jb * 8u;
+        if (ncc == GW_MAXNB) {
 #pragma unroll 1
-        for (int j = jb; j < je; j += 2) {
-          const double2 a0 = *reinterpret_cast<const double2 *>(ap + (size_t)j * ld);
-          const double2 b0 = *reinterpret_cast<const double2 *>(ap + (size_t)j * ld + hb);
-          const double2 a1 = *reinterpret_cast<const double2 *>(ap + (size_t)(j + 1) * ld);
-          const double2 b1 = *reinterpret_cast<const double2 *>(ap + (size_t)(j + 1) * ld + hb);
+          for (int j = jb; j < je; j += 2, ap += 2 * rowb, joff += 16) {
+            const double2 a0 = lds_f64x2(ap), b0 = lds_f64x2(ap + hb), a1 = lds_f64x2(ap + rowb), b1 = lds_f64x2(ap + rowb + hb);
+            double2 x[GW_MAXNB];
 #pragma unroll
-          for (int cc = 0; cc < TC; ++cc) {
-            const double2 x = *reinterpret_cast<const double2 *>(xp + (size_t)cc * ld + j);
-            acc[0][cc] = fma(a0.x, x.x, acc[0][cc]); acc[1][cc] = fma(a0.y, x.x, acc[1][cc]);
-            acc[2][cc] = fma(b0.x, x.x, acc[2][cc]); acc[3][cc] = fma(b0.y, x.x, acc[3][cc]);
-            acc[0][cc] = fma(a1.x, x.y, acc[0][cc]); acc[1][cc] = fma(a1.y, x.y, acc[1][cc]);
-            acc[2][cc] = fma(b1.x, x.y, acc[2][cc]); acc[3][cc] = fma(b1.y, x.y, acc[3][cc]);
+            for (int cc = 0; cc < GW_MAXNB; ++cc) x[cc] = lds_f64x2(xaddr[cc] + joff);
+#pragma unroll
+            for (int cc = 0; cc < GW_MAXNB; ++cc) {
+              acc[0][cc] = fma(a0.x, x[cc].x, acc[0][cc]); acc[1][cc] = fma(a0.y, x[cc].x, acc[1][cc]);
+              acc[2][cc] = fma(b0.x, x[cc].x, acc[2][cc]); acc[3][cc] = fma(b0.y, x[cc].x, acc[3][cc]);
+            }
+#pragma unroll
+            for (int cc = 0; cc < GW_MAXNB; ++cc) {
+              acc[0][cc] = fma(a1.x, x[cc].y, acc[0][cc]); acc[1][cc] = fma(a1.y, x[cc].y, acc[1][cc]);
+              acc[2][cc] = fma(b1.x, x[cc].y, acc[2][cc]); acc[3][cc] = fma(b1.y, x[cc].y, acc[3][cc]);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int j = jb; j < je; j += 2, ap += 2 * rowb, joff += 16) {
+            const double2 a0 = lds_f64x2(ap), b0 = lds_f64x2(ap + hb), a1 = lds_f64x2(ap + rowb), b1 = lds_f64x2(ap + rowb + hb);
+            double2 x[GW_MAXNB + 1];
+#pragma unroll
+            for (int cc = 0; cc <= GW_MAXNB; ++cc) x[cc] = lds_f64x2(xaddr[cc] + joff);
+#pragma unroll
+            for (int cc = 0; cc <= GW_MAXNB; ++cc) {
+              acc[0][cc] = fma(a0.x, x[cc].x, acc[0][cc]); acc[1][cc] = fma(a0.y, x[cc].x, acc[1][cc]);
+              acc[2][cc] = fma(b0.x, x[cc].x, acc[2][cc]); acc[3][cc] = fma(b0.y, x[cc].x, acc[3][cc]);
+            }
+#pragma unroll
+            for (int cc = 0; cc <= GW_MAXNB; ++cc) {
+              acc[0][cc] = fma(a1.x, x[cc].y, acc[0][cc]); acc[1][cc] = fma(a1.y, x[cc].y, acc[1][cc]);
+              acc[2][cc] = fma(b1.x, x[cc].y, acc[2][cc]); acc[3][cc] = fma(b1.y, x[cc].y, acc[3][cc]);
+            }
           }
         }
       }
-      __syncthreads();   // every column has been read: the products may now overwrite them in place
-      if (pass == 0) GW_STAMP();   // +3: products computed
+      group_sync(gid);   // every column of the group has been read: the products may now overwrite them in place
+      GW_STAMP();   // +3: products computed
 #pragma unroll 1
       for (int r = 0; r < GW_KS; ++r) {
         if (active && ks == r) {
-          double *wp = Wc + (size_t)colbase * ld + 2 * lane;
-          const int hb = ld / 2;
-          if (r > 0) {
+          const uint32_t hb = (uint32_t)ld * 4u;
 #pragma unroll
-            for (int cc = 0; cc < TC; ++cc) {
-              const double2 ta = *reinterpret_cast<const double2 *>(wp + (size_t)cc * ld);
-              const double2 tb = *reinterpret_cast<const double2 *>(wp + (size_t)cc * ld + hb);
-              acc[0][cc] = ta.x + acc[0][cc]; acc[1][cc] = ta.y + acc[1][cc];
-              acc[2][cc] = tb.x + acc[2][cc]; acc[3][cc] = tb.y + acc[3][cc];
+          for (int cc = 0; cc <= GW_MAXNB; ++cc) {
+            if (cc < nb || (cc == nb && do_refresh)) {
+              const uint32_t wp = xaddr[cc] + 16u * (uint32_t)lane;
+              if (r > 0) {
+                const double2 ta = lds_f64x2(wp), tb = lds_f64x2(wp + hb);
+                acc[0][cc] = ta.x + acc[0][cc]; acc[1][cc] = ta.y + acc[1][cc];
+                acc[2][cc] = tb.x + acc[2][cc]; acc[3][cc] = tb.y + acc[3][cc];
+              }
+              sts_f64x2(wp, acc[0][cc], acc[1][cc]);
+              sts_f64x2(wp + hb, acc[2][cc], acc[3][cc]);
             }
           }
-#pragma unroll
-          for (int cc = 0; cc < TC; ++cc) {
-            *reinterpret_cast<double2 *>(wp + (size_t)cc * ld) = make_double2(acc[0][cc], acc[1][cc]);
-            *reinterpret_cast<double2 *>(wp + (size_t)cc * ld + hb) = make_double2(acc[2][cc], acc[3][cc]);
-          }
         }
-        __syncthreads();
+        group_sync(gid);
       }
     }
     GW_STAMP();   // +4: products written
     // ================================================================ C: the chains (warp per chain)
-    if (warp < nch) {
-      const int c_local = cta_chain0 + warp;
+    if (gw < gch) {
+      const int cs = gfirst + gw;                 // chain slot in the CTA
+      const int c_local = cta_chain0 + cs;
       const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + c_local);
       double x0[4] = {0, 0, 0, 0}, y0[4] = {0, 0, 0, 0};
-      double Q0 = cst[warp * 4], last_prior = cst[warp * 4 + 1], last_like = cst[warp * 4 + 2];
+      double Q0 = cst[cs * 4], last_prior = cst[cs * 4 + 1], last_like = cst[cs * 4 + 2];
       if (own) {
-        const double2 a = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0), b = *reinterpret_cast<const double2 *>(Xs + warp * ld + i0 + 2);
+        const double2 a = *reinterpret_cast<const double2 *>(Xs + cs * ld + i0), b = *reinterpret_cast<const double2 *>(Xs + cs * ld + i0 + 2);
         x0[0] = a.x; x0[1] = a.y; x0[2] = b.x; x0[3] = b.y;
       }
       if (do_refresh) {
-        const double *ws = Wc + (size_t)(ncol + warp) * ld + i0;
+        const double *ws = Wc + (size_t)(ncol + cs) * ld + i0;
         double part = 0.0;
         if (own) {
           const double2 a = *reinterpret_cast<const double2 *>(ws), b = *reinterpret_cast<const double2 *>(ws + 2);
@@ -403,7 +432,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
         }
         Q0 = gsum<32>(part, 0xffffffffu);
       } else if (own) {
-        const double2 a = *reinterpret_cast<const double2 *>(Ys + warp * ld + i0), b = *reinterpret_cast<const double2 *>(Ys + warp * ld + i0 + 2);
+        const double2 a = *reinterpret_cast<const double2 *>(Ys + cs * ld + i0), b = *reinterpret_cast<const double2 *>(Ys + cs * ld + i0 + 2);
         y0[0] = a.x; y0[1] = a.y; y0[2] = b.x; y0[3] = b.y;
       }
       double ntn_last = nan_to_num(1.0 * last_like + last_prior);
@@ -412,7 +441,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
       uint32_t mt = 0;
       double lu = 0.0, gsnk = 0.0, sd = 0.0;
       auto load_col = [&](int itb, double (&aa)[4], double (&bb)[4], double (&ww)[4], uint32_t &m, double &l, double &g) {
-        const int col = itb * TC + warp;
+        const int col = gbase + gw * NB + itb;
         if (own) {
           const double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
           const double2 j01 = *reinterpret_cast<const double2 *>(js), j23 = *reinterpret_cast<const double2 *>(js + 2);
@@ -549,19 +578,20 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
       }
       // park the chain state for the next batch / the epilogue
       if (own) {
-        *reinterpret_cast<double2 *>(Xs + warp * ld + i0) = make_double2(x0[0], x0[1]);
-        *reinterpret_cast<double2 *>(Xs + warp * ld + i0 + 2) = make_double2(x0[2], x0[3]);
-        *reinterpret_cast<double2 *>(Ys + warp * ld + i0) = make_double2(y0[0], y0[1]);
-        *reinterpret_cast<double2 *>(Ys + warp * ld + i0 + 2) = make_double2(y0[2], y0[3]);
+        *reinterpret_cast<double2 *>(Xs + cs * ld + i0) = make_double2(x0[0], x0[1]);
+        *reinterpret_cast<double2 *>(Xs + cs * ld + i0 + 2) = make_double2(x0[2], x0[3]);
+        *reinterpret_cast<double2 *>(Ys + cs * ld + i0) = make_double2(y0[0], y0[1]);
+        *reinterpret_cast<double2 *>(Ys + cs * ld + i0 + 2) = make_double2(y0[2], y0[3]);
       }
-      if (lane == 0) { cst[warp * 4] = Q0; cst[warp * 4 + 1] = last_prior; cst[warp * 4 + 2] = last_like; }
+      if (lane == 0) { cst[cs * 4] = Q0; cst[cs * 4 + 1] = last_prior; cst[cs * 4 + 2] = last_like; }
     }
     GW_STAMP();   // +5: chain of warp 0 advanced
     done += nb;
-    __syncthreads();   // the slots are free for the next batch
+    group_sync(gid);   // the group's slots are free for the next batch
   }
   GW_STAMP();
-  if (warp < nch) {
+  __syncthreads();
+  if (warp < nch_cta) {
     const int c_local = cta_chain0 + warp;
     if (own) {
       double *xrow = P.st.X + (size_t)c_local * ld + i0, *yrow = P.st.gauss_Y + (size_t)c_local * ld + i0;
@@ -578,11 +608,13 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
   }
 }
 
-// largest batch (iterations) whose tiles fit the CTA's warps and whose buffers fit shared memory; 0 = kernel not usable
+// largest batch (iterations) whose tiles fit a group's warps and whose buffers fit shared memory; 0 = kernel not usable
 inline int gwin_pick_nb(const dreamzs_config &cfg, int TC, size_t *smem_bytes) {
   if (cfg.ld > 128 || (cfg.ld & 3)) return 0;
+  const int gc = gwin_group_chains(TC, 0);
+  if (gc * GW_KS > GW_GWARPS) return 0;
   for (int nb = GW_MAXNB; nb >= 1; --nb) {
-    if (nb * GW_KS > GW_WARPS || (nb * TC + GW_WARPS - 1) / GW_WARPS > GW_MAXCOLW) continue;
+    if ((gc * nb + GW_GWARPS - 1) / GW_GWARPS > GW_MAXCOLW) continue;
     const GwinLayout L = gwin_layout(cfg.ndim, cfg.ld, TC, nb, cfg.ngamma);
     if (L.bytes <= 227 * 1024) { *smem_bytes = L.bytes; return nb; }
   }
