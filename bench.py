@@ -239,6 +239,9 @@ def bench_gpu(args):
     ms = float(t.item())
     value = N * K / (ms * 1e-3)
     acc_check = float(logp[:, -1].mean().item())   # touch the result
+    eng.check_peers()
+    transport = 'nvlink peer stores' if eng.peers is not None else ('nccl all-gather' if world > 1 else 'none')
+    eng.close()
     del trace, logp
 
     # ---------------- end to end through the public API with host buffers
@@ -290,7 +293,7 @@ def bench_gpu(args):
                                          'DE/snooker proposal + logp + accept kernel',
                                 ndim=D, nchains=N, chains_per_gpu=CHAINS_PER_GPU, archive_seed_rows=NSEED,
                                 l2_policy='inputs larger than L2: archive >= 210 MB, gathered rows are random',
-                                fused_iterations_per_launch=thin, e2e_steps=Ke, **OPTS),
+                                fused_iterations_per_launch=thin, e2e_steps=Ke, archive_replication=transport, **OPTS),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit='chain-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              seconds=e2e_s, steps=Ke, api='pydream_b200.core.run_dream (numpy in, numpy out)'),

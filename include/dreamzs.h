@@ -45,6 +45,7 @@ extern "C" {
 #define DREAMZS_MAX_MULTITRY 16
 #define DREAMZS_MAX_NDIM 1024
 #define DREAMZS_GAUSS_REFRESH_WINDOWS 4
+#define DREAMZS_MAX_PEERS 8
 
 /* dreamzs_config.flags */
 #define DREAMZS_FLAG_ALL_FLAT 1  /* every prior is FLAT: the kernels skip prior evaluation and bounds */
@@ -147,16 +148,44 @@ int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state *st, void *
 int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                  int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream);
 
+/* Replicas of the archive on the other GPUs of the box (pydream/Dream_shared_vars.py `history` is ONE shared
+ * array in the reference; here every GPU holds a copy and the copies are kept identical over NVLink).
+ * Z[q] / flags[q] are rank q's archive and flag array (DREAMZS_MAX_PEERS uint64, zero-initialised) as mapped
+ * into THIS process (cudaIpcOpenMemHandle, see dreamzs_shared_*); Z[rank] must equal dreamzs_state.Z.
+ * With peers, the appending iteration of a launch stores every local chain's row into all replicas (plain
+ * peer stores from the step kernel), dreamzs_run then publishes "append #k done" into flags[q][rank] of
+ * every peer (system-scope release) and waits, before a launch that may sample those rows, until every
+ * flags[rank][q] has reached k (acquire; the wait gives up after DREAMZS_PEER_TIMEOUT_NS and sets *error). */
+typedef struct dreamzs_peers {
+  int32_t world, rank;
+  double *Z[DREAMZS_MAX_PEERS];
+  uint64_t *flags[DREAMZS_MAX_PEERS];
+  int32_t *error;            /* device int32 of this rank, zero-initialised; 1 after a timed-out wait */
+} dreamzs_peers;
+#define DREAMZS_PEER_TIMEOUT_NS 10000000000ull
+
+/* Device memory that other processes of the box can map: cudaMalloc + cudaIpcGetMemHandle (zero-filled),
+ * cudaIpcOpenMemHandle (peer access enabled lazily), and their inverses.  `handle` is the 64-byte
+ * cudaIpcMemHandle_t.  These are the only entry points that allocate; the caller owns the result. */
+int dreamzs_shared_alloc(int64_t bytes, void **dev_ptr, void *handle);
+int dreamzs_shared_open(const void *handle, void **dev_ptr);
+int dreamzs_shared_close(void *dev_ptr);
+int dreamzs_shared_free(void *dev_ptr);
+
 /* The chain loop of _sample_dream (pydream/core.py:103-122) for iterations that need no host decision between
  * them (no adaptation): iterations iter_begin .. iter_begin+niter-1 as one dreamzs_step launch per window, a
  * window ending at an iteration t with t % history_thin == 0.  tr->trace_offset is the trace row of
- * iter_begin.  After each appending launch `hook(user, first_row, nrows)` is called on the host (it may
- * enqueue stream-ordered work, e.g. the all-gather of the other shards' rows; it must return 0); hook may be
- * NULL when nchains_local == nchains_global.  *launches (optional) receives the number of kernel launches,
- * *archive_rows_out (optional) the archive size after the run. */
+ * iter_begin.  `appends_done` = number of appends made so far (archive_rows = seed rows + appends_done *
+ * nchains_global).  Sharded runs keep the replicas of the archive identical either through `peers`
+ * (NVLink peer stores, see dreamzs_peers) or, when peers is NULL, through `hook(user, first_row, nrows)`,
+ * called on the host after each appending launch (it may enqueue stream-ordered work, e.g. an NCCL all-gather
+ * of the other shards' rows; it must return 0).  Both may be NULL when nchains_local == nchains_global.
+ * *launches (optional) receives the number of kernel launches, *archive_rows_out (optional) the archive
+ * size after the run. */
 typedef int (*dreamzs_append_hook)(void *user, int64_t first_row, int64_t nrows);
 int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
-                int64_t iter_begin, int64_t niter, int64_t archive_rows, dreamzs_append_hook hook, void *user,
+                int64_t iter_begin, int64_t niter, int64_t archive_rows, int64_t appends_done,
+                const dreamzs_peers *peers, dreamzs_append_hook hook, void *user,
                 void *stream, int64_t *launches, int64_t *archive_rows_out);
 
 /* sampled_params / log_ps leave the device (pydream/core.py:81-86 returns them to the caller): stream-ordered

@@ -18,7 +18,8 @@ FLAG_GENERIC_KERNEL = 2
 FLAG_NO_WINDOW_KERNEL = 4
 PRIOR_FLAT, PRIOR_NORMAL, PRIOR_UNIFORM = 0, 1, 2
 
-EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_run', 'dreamzs_copy_d2h_2d', 'dreamzs_adapt_workspace_bytes',
+EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_run', 'dreamzs_copy_d2h_2d',
+           'dreamzs_shared_alloc', 'dreamzs_shared_open', 'dreamzs_shared_close', 'dreamzs_shared_free', 'dreamzs_adapt_workspace_bytes',
            'dreamzs_adapt_colsum', 'dreamzs_adapt_colsq', 'dreamzs_adapt_jumps', 'dreamzs_adapt_finish',
            'dreamzs_gr_chain_stats', 'dreamzs_gr_finish']
 
@@ -42,6 +43,14 @@ class State(C.Structure):
 class Trace(C.Structure):
     _fields_ = [('trace', C.c_void_p), ('trace_logp', C.c_void_p), ('decisions', C.c_void_p),
                 ('trace_iters', C.c_int64), ('trace_offset', C.c_int64)]
+
+
+MAX_PEERS = 8
+
+
+class Peers(C.Structure):
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('Z', C.c_void_p * MAX_PEERS), ('flags', C.c_void_p * MAX_PEERS),
+                ('error', C.c_void_p)]
 
 
 APPEND_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64)
@@ -69,7 +78,12 @@ def load():
         'dreamzs_abi_version': (C.c_int, []),
         'dreamzs_init_logp': (C.c_int, [cfgp, stp, vp]),
         'dreamzs_step': (C.c_int, [cfgp, stp, trp, i64, i32, i64, vp]),
-        'dreamzs_run': (C.c_int, [cfgp, stp, trp, i64, i64, i64, APPEND_HOOK, vp, vp, C.POINTER(i64), C.POINTER(i64)]),
+        'dreamzs_run': (C.c_int, [cfgp, stp, trp, i64, i64, i64, i64, C.POINTER(Peers), APPEND_HOOK, vp, vp, C.POINTER(i64),
+                                  C.POINTER(i64)]),
+        'dreamzs_shared_alloc': (C.c_int, [i64, C.POINTER(vp), vp]),
+        'dreamzs_shared_open': (C.c_int, [vp, C.POINTER(vp)]),
+        'dreamzs_shared_close': (C.c_int, [vp]),
+        'dreamzs_shared_free': (C.c_int, [vp]),
         'dreamzs_copy_d2h_2d': (C.c_int, [vp, i64, vp, i64, i64, i64, vp]),
         'dreamzs_adapt_workspace_bytes': (i64, [cfgp]),
         'dreamzs_adapt_colsum': (C.c_int, [cfgp, vp, vp, vp, vp]),

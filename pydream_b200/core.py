@@ -173,8 +173,11 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
             step_instance.save_history_to_disc(eng.history_flat()[:ref_rows * d], prefix)
 
     if return_device:
-        return trace, logp
+        eng.check_peers()
+        return trace, logp     # (a sharded caller keeps `trace` alive; the shared archive is released with the engine)
     torch.cuda.current_stream(eng.device).synchronize()
+    eng.check_peers()
+    eng.close()
     t_d = time.perf_counter()
     tr_np, lp_np = tr_host.numpy(), lp_host.numpy()
     sampled_params = [tr_np[c] for c in range(eng.Nl)]

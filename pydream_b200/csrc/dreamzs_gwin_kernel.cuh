@@ -562,6 +562,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
             double *zr = P.st.Z + (size_t)(M + c_global) * ld + i0;
             *reinterpret_cast<double2 *>(zr) = make_double2(x0[0], x0[1]);
             *reinterpret_cast<double2 *>(zr + 2) = make_double2(x0[2], x0[3]);
+            for (int pz = 0; pz < P.npeers; ++pz) {   // replicas over NVLink
+              double *zp = P.peer_Z[pz] + (size_t)(M + c_global) * ld + i0;
+              *reinterpret_cast<double2 *>(zp) = make_double2(x0[0], x0[1]);
+              *reinterpret_cast<double2 *>(zp + 2) = make_double2(x0[2], x0[3]);
+            }
           }
         }
         if (lane == 0) {

@@ -598,7 +598,10 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
             pack_decision(changed, dc.run_snooker, dc.cr_idx, dc.lvl_idx, dc.delta, sel, gamma_one, accepted);
     }
     // record_history (Dream.py:360-362, 919-938): only the last iteration of a launch may append
-    if (iter % P.cfg.history_thin == 0) store_row<G, R>(c, P.st.Z + (size_t)(M + c_global) * ld, x0);
+    if (iter % P.cfg.history_thin == 0) {
+      store_row<G, R>(c, P.st.Z + (size_t)(M + c_global) * ld, x0);
+      for (int pz = 0; pz < P.npeers; ++pz) store_row<G, R>(c, P.peer_Z[pz] + (size_t)(M + c_global) * ld, x0);   // replicas over NVLink
+    }
     __syncwarp(c.gmask);
   }
   store_row<G, R>(c, P.st.X + (size_t)c_local * ld, x0);

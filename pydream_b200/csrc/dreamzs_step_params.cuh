@@ -17,6 +17,8 @@ struct StepParams {
   int32_t nslots;         // proposal slots per chain in shared memory
   int32_t init_only;      // dreamzs_init_logp: evaluate logp(X) and return
   int32_t gw_nb;          // window kernel: iterations per batch
+  int32_t npeers;         // other GPUs holding a replica of the archive (NVLink peer mappings)
+  double *peer_Z[DREAMZS_MAX_PEERS];   // their Z, as mapped in this process
   long long *dbg;         // optional phase-timestamp buffer (dreamzs_debug_set_phase_buffer; profiling aid)
   int32_t gw_append;      // window kernel: the last iteration of the launch appends to the archive
   int32_t gw_refresh;     // window kernel: re-derive gauss_Y / gauss_Q from X at the start of the launch

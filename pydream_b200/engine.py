@@ -26,6 +26,16 @@ from . import targets as T
 from .collectives import allgather_rows, allreduce_sum
 
 
+SHARED_HEADER = 4096      # bytes in front of a shared archive block: flags (8 x uint64) at 0, error word at 1024
+
+
+class _DevicePtr:
+    """Raw device memory (owned elsewhere) exposed through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = dict(shape=(int(nbytes),), typestr='|u1', data=(int(ptr), False), version=2)
+
+
 def round_up4(d):
     return (int(d) + 3) // 4 * 4
 
@@ -81,7 +91,7 @@ class DreamEngine:
                  nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
                  history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
                  cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True,
-                 generic_kernel=False, window_kernel=True, reserve_iters=0):
+                 generic_kernel=False, window_kernel=True, reserve_iters=0, peer_archive=True):
         if not torch.cuda.is_available():
             raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _cabi.load()
@@ -107,6 +117,11 @@ class DreamEngine:
         self.iter = 0
         self._hist_host = history
         self.Z = None
+        # sharded runs keep the archive replicas identical with NVLink peer stores (dreamzs_peers) when the ranks can
+        # map each other's memory, else with an NCCL all-gather per append
+        self.peers = None
+        self._shared = None          # (own base pointer, [opened peer base pointers])
+        self._want_peers = bool(peer_archive) and self.world > 1 and self.world <= _cabi.MAX_PEERS
         # the archive is sized once for `reserve_iters` iterations (it grows on demand beyond that)
         self._ensure_capacity(self.nseed + appends_in(0, int(reserve_iters), self.thin) * N)
         starts = np.asarray(starts, dtype=np.float64).reshape(N, d)
@@ -167,11 +182,16 @@ class DreamEngine:
                               gauss_Q=p(self.gauss_Q) if self.gauss_Q is not None else None)
 
     def _ensure_capacity(self, rows):
+        """Make room for `rows` archive rows.  Collective when the archive is shared between ranks."""
         if self.Z is not None and self.Z.shape[0] >= rows:
             return
-        # rows past the current size are written (record_history) before they can be sampled: no zero-fill
-        Z = torch.empty((rows, self.ld), dtype=torch.float64, device=self.device)
-        if self.Z is None:
+        old = self.Z
+        if self._want_peers:
+            Z = self._alloc_shared(rows)
+        else:
+            # rows past the current size are written (record_history) before they can be sampled: no zero-fill
+            Z = torch.empty((rows, self.ld), dtype=torch.float64, device=self.device)
+        if old is None:
             # seed rows: one host->device copy of the caller's array (asynchronous when it lives in pinned memory),
             # padded to the row stride on the device
             h = torch.from_numpy(np.ascontiguousarray(self._hist_host))
@@ -183,10 +203,95 @@ class DreamEngine:
                 Z[:self.nseed, self.d:] = 0
             self._hist_host = None
         else:
-            Z[:self.archive_rows] = self.Z[:self.archive_rows]
+            Z[:self.archive_rows] = old[:self.archive_rows]
         self.Z = Z
+        if self.peers is not None:
+            self._finish_shared()
         if hasattr(self, 'st'):
             self._state()
+
+    def _alloc_shared(self, rows):
+        """Archive block other ranks can map (dreamzs_shared_alloc + handle exchange).  Falls back to a private
+        archive + NCCL all-gather (for every rank alike) when a mapping cannot be made."""
+        dist = torch.distributed
+        lib = self.lib
+        nbytes = SHARED_HEADER + rows * self.ld * 8
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)                      # nobody is still writing into the block being replaced
+        base, handle = C.c_void_p(), C.create_string_buffer(64)
+        ok = lib.dreamzs_shared_alloc(nbytes, C.byref(base), handle) == _cabi.OK
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw if ok else None, group=self.group)
+        opened = []
+        if ok and all(h is not None for h in handles):
+            for q, h in enumerate(handles):
+                if q == self.rank:
+                    opened.append(base.value)
+                    continue
+                pq = C.c_void_p()
+                if lib.dreamzs_shared_open(C.create_string_buffer(h, 64), C.byref(pq)) != _cabi.OK:
+                    ok = False
+                    break
+                opened.append(pq.value)
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:                     # some rank cannot map a peer: every rank uses NCCL
+            for q, pq in enumerate(opened):
+                if q != self.rank:
+                    lib.dreamzs_shared_close(C.c_void_p(pq))
+            if base.value:
+                lib.dreamzs_shared_free(base)
+            self._want_peers = False
+            return torch.empty((rows, self.ld), dtype=torch.float64, device=self.device)
+        block = torch.as_tensor(_DevicePtr(base.value, nbytes), device=self.device)
+        if self._shared is not None:                  # growing: the flags published so far carry over
+            old_block = self._shared['block']
+            block[:SHARED_HEADER].copy_(old_block[:SHARED_HEADER])
+        self._shared_new = dict(base=base.value, opened=opened, block=block)
+        pr = _cabi.Peers(world=self.world, rank=self.rank)
+        for q, pq in enumerate(opened):
+            pr.Z[q] = pq + SHARED_HEADER
+            pr.flags[q] = pq
+        pr.error = base.value + 1024
+        self.peers = pr
+        return block[SHARED_HEADER:].view(torch.float64).view(rows, self.ld)
+
+    def _finish_shared(self):
+        """Second half of a (re)allocation of the shared archive: every rank's block is filled, then the old
+        mappings go away."""
+        if not hasattr(self, '_shared_new') or self._shared_new is None:
+            return
+        torch.cuda.synchronize(self.device)
+        torch.distributed.barrier(self.group)         # every replica holds its seed rows / old contents
+        self._release_shared()
+        self._shared, self._shared_new = self._shared_new, None
+
+    def _release_shared(self):
+        if self._shared is None:
+            return
+        for q, pq in enumerate(self._shared['opened']):
+            if q != self.rank:
+                self.lib.dreamzs_shared_close(C.c_void_p(pq))
+        self.lib.dreamzs_shared_free(C.c_void_p(self._shared['base']))
+        self._shared = None
+
+    def close(self):
+        """Collective: unmap the peers' archives and free the shared block (no-op for private archives)."""
+        if self._shared is not None:
+            torch.cuda.synchronize(self.device)
+            torch.distributed.barrier(self.group)
+            self.Z = None
+            self.peers = None
+            self._release_shared()
+
+    def check_peers(self):
+        """Raise if a wait for a peer's append timed out (DREAMZS_PEER_TIMEOUT_NS)."""
+        if self._shared is not None:
+            err = self._shared['block'][1024:1028].view(torch.int32)
+            if int(err.item()) != 0:
+                raise _cabi.DreamzsError('timed out waiting for a peer GPU to publish its archive append')
 
     @property
     def archive_rows(self):
@@ -220,27 +325,27 @@ class DreamEngine:
         cfg, st = C.byref(self.cfg), C.byref(self.st)
         t_first, end = self.iter, self.iter + niter
         t = self.iter
-        if adapting and t <= self.crossover_burnin:
-            self._x_entry = self.X.clone()
-            while t < end and t <= self.crossover_burnin:
-                tr.trace_offset = t - t_first
-                rc = self.lib.dreamzs_step(cfg, st, C.byref(tr), t, 1, self.archive_rows, stream)
-                _cabi.check(rc, 'dreamzs_step')
-                self.launches += 1
-                if (10 < t < self.crossover_burnin) or t == self.crossover_burnin:
-                    self._adapt(trace, decisions, t - t_first, t == self.crossover_burnin)
-                if t % self.thin == 0:
-                    self._publish_append()
-                t += 1
-        if t < end:
-            tr.trace_offset = t - t_first
+        hook = self._hook if (self.world > 1 and self.peers is None) else _cabi.APPEND_HOOK()
+        peers = C.byref(self.peers) if self.peers is not None else None
+
+        def native(t0, n):
+            tr.trace_offset = t0 - t_first
             nl, rows = C.c_int64(0), C.c_int64(0)
-            hook = self._hook if self.world > 1 else _cabi.APPEND_HOOK()
-            rc = self.lib.dreamzs_run(cfg, st, C.byref(tr), t, end - t, self.archive_rows, hook, None, stream,
-                                      C.byref(nl), C.byref(rows))
+            rc = self.lib.dreamzs_run(cfg, st, C.byref(tr), t0, n, self.archive_rows, self.count // self.N, peers, hook,
+                                      None, stream, C.byref(nl), C.byref(rows))
             _cabi.check(rc, 'dreamzs_run')
             self.launches += int(nl.value)
             self.count = int(rows.value) - self.nseed
+
+        if adapting and t <= self.crossover_burnin:
+            self._x_entry = self.X.clone()
+            while t < end and t <= self.crossover_burnin:
+                native(t, 1)
+                if (10 < t < self.crossover_burnin) or t == self.crossover_burnin:
+                    self._adapt(trace, decisions, t - t_first, t == self.crossover_burnin)
+                t += 1
+        if t < end:
+            native(t, end - t)
         self.iter = end
 
     def run_to_host(self, niter, out_params, out_logp, chunk_iters=256, on_chunk=None):
@@ -302,12 +407,6 @@ class DreamEngine:
             import traceback
             traceback.print_exc()
             return _cabi.E_LAUNCH
-
-    def _publish_append(self):
-        """record_history for the whole sweep: the kernel wrote the local rows; gather the others."""
-        M = self.archive_rows
-        allgather_rows(self.Z[M:M + self.N], self.c0, self.Nl, self.group)
-        self.count += self.N
 
     def _allreduce(self, t):
         allreduce_sum(t, self.group)

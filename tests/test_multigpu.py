@@ -26,7 +26,7 @@ def _inputs(case):
     return make_target(dict(kind=case['target'], d=d)), hist, hist[:N].copy()
 
 
-def _worker(rank, world, port, name, out):
+def _worker(rank, world, port, name, out, peer_archive):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import torch
@@ -37,18 +37,25 @@ def _worker(rank, world, port, name, out):
     from pydream_b200.engine import DreamEngine
     case = CASES[name]
     tgt, hist, starts = _inputs(case)
-    eng = DreamEngine(case['d'], case['N'], hist, starts, tgt, seed=4, group=dist.group.WORLD, **case['kw'])
-    trace, logp, dec = eng.run(case['T'])
+    eng = DreamEngine(case['d'], case['N'], hist, starts, tgt, seed=4, group=dist.group.WORLD, peer_archive=peer_archive,
+                      **case['kw'])
+    # two calls: the archive grows between them (collective re-allocation of the shared block)
+    T1 = case['T'] // 3
+    parts = [eng.run(T1), eng.run(case['T'] - T1)]
+    trace, logp, dec = (torch.cat([a[i] for a in parts], dim=1) for i in range(3))
     rhat = eng.gelman_rubin(trace)
     torch.cuda.synchronize()
+    eng.check_peers()
     torch.save(dict(trace=trace.cpu(), logp=logp.cpu(), dec=dec.cpu(), Z=eng.Z[:eng.archive_rows].cpu(),
-                    cr=eng.cr_probs.cpu(), rhat=rhat.cpu()), out % rank)
+                    cr=eng.cr_probs.cpu(), rhat=rhat.cpu(), peers=eng.peers is not None), out % rank)
+    eng.close()
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('peer_archive', [True, False], ids=['nvlink_peer_stores', 'nccl_allgather'])
 @pytest.mark.parametrize('name', sorted(CASES))
-def test_sharded_equals_single_gpu(name, tmp_path):
+def test_sharded_equals_single_gpu(name, peer_archive, tmp_path):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -60,12 +67,13 @@ def test_sharded_equals_single_gpu(name, tmp_path):
     trace, logp, dec = eng.run(case['T'])
     rhat = eng.gelman_rubin(trace).cpu()
     out = str(tmp_path / 'rank%d.pt')
-    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, name, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, name, out, peer_archive), nprocs=2, join=True)
     parts = [torch.load(out % r) for r in range(2)]
     assert torch.equal(torch.cat([p['trace'] for p in parts]), trace.cpu())
     assert torch.equal(torch.cat([p['logp'] for p in parts]), logp.cpu())
     assert torch.equal(torch.cat([p['dec'] for p in parts]), dec.cpu())
     for p in parts:   # every rank holds the full archive, identical to the single-GPU one
+        assert p['peers'] == peer_archive
         assert torch.equal(p['Z'], eng.Z[:eng.archive_rows].cpu())
         np.testing.assert_allclose(p['cr'].numpy(), eng.cr_probs.cpu().numpy(), rtol=1e-12)
         np.testing.assert_allclose(p['rhat'].numpy(), rhat.numpy(), rtol=1e-12)
