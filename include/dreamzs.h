@@ -153,13 +153,16 @@ int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dream
  * Z[q] / flags[q] are rank q's archive and flag array (DREAMZS_MAX_PEERS uint64, zero-initialised) as mapped
  * into THIS process (cudaIpcOpenMemHandle, see dreamzs_shared_*); Z[rank] must equal dreamzs_state.Z.
  * With peers, the appending iteration of a launch stores every local chain's row into all replicas (plain
- * peer stores from the step kernel), dreamzs_run then publishes "append #k done" into flags[q][rank] of
- * every peer (system-scope release) and waits, before a launch that may sample those rows, until every
- * flags[rank][q] has reached k (acquire; the wait gives up after DREAMZS_PEER_TIMEOUT_NS and sets *error). */
+ * peer stores from the step kernel, each followed by a system-scope fence); the chain that completes the
+ * launch's appends publishes "append #k done" into flags[q][rank] of every peer (st.release.sys), and the
+ * next launch that may sample those rows first waits until every flags[rank][q] has reached k
+ * (ld.acquire.sys; the wait gives up after DREAMZS_PEER_TIMEOUT_NS and sets *error).  Compute and the
+ * exchange are one kernel: no collective call and no extra launch per window. */
 typedef struct dreamzs_peers {
   int32_t world, rank;
   double *Z[DREAMZS_MAX_PEERS];
   uint64_t *flags[DREAMZS_MAX_PEERS];
+  uint32_t *counter;         /* device uint32 of this rank, zero-initialised: chains that have appended (scratch) */
   int32_t *error;            /* device int32 of this rank, zero-initialised; 1 after a timed-out wait */
 } dreamzs_peers;
 #define DREAMZS_PEER_TIMEOUT_NS 10000000000ull

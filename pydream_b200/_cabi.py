@@ -50,7 +50,7 @@ MAX_PEERS = 8
 
 class Peers(C.Structure):
     _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('Z', C.c_void_p * MAX_PEERS), ('flags', C.c_void_p * MAX_PEERS),
-                ('error', C.c_void_p)]
+                ('counter', C.c_void_p), ('error', C.c_void_p)]
 
 
 APPEND_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64)

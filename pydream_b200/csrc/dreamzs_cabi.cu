@@ -121,15 +121,17 @@ extern "C" int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state 
 }
 
 static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter_begin,
-                     int32_t niter, int64_t archive_rows, const dreamzs_peers *peers, void *stream);
+                     int32_t niter, int64_t archive_rows, const dreamzs_peers *peers, uint64_t wait_k, uint64_t publish_k,
+                     void *stream);
 
 extern "C" int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                             int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream) {
-  return step_impl(cfg, st, tr, iter_begin, niter, archive_rows, nullptr, stream);
+  return step_impl(cfg, st, tr, iter_begin, niter, archive_rows, nullptr, 0, 0, stream);
 }
 
 static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter_begin,
-                     int32_t niter, int64_t archive_rows, const dreamzs_peers *peers, void *stream) {
+                     int32_t niter, int64_t archive_rows, const dreamzs_peers *peers, uint64_t wait_k, uint64_t publish_k,
+                     void *stream) {
   int rc = check_cfg(cfg, st);
   if (rc != DREAMZS_OK) return rc;
   if (!tr || !tr->trace || !tr->trace_logp || niter < 0 || iter_begin < 0) return DREAMZS_E_BADARG;
@@ -149,49 +151,18 @@ static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const d
     if (peers->world < 1 || peers->world > DREAMZS_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) return DREAMZS_E_BADARG;
     for (int q = 0; q < peers->world; ++q)
       if (q != peers->rank) {
-        if (!peers->Z[q]) return DREAMZS_E_BADARG;
+        if (!peers->Z[q] || !peers->flags[q]) return DREAMZS_E_BADARG;
+        P.peer_flag[P.npeers] = peers->flags[q] + peers->rank;
         P.peer_Z[P.npeers++] = peers->Z[q];
       }
+    if (!peers->flags[peers->rank] || !peers->counter || !peers->error) return DREAMZS_E_BADARG;
+    P.my_flags = peers->flags[peers->rank]; P.my_rank = peers->rank; P.world = peers->world;
+    P.wait_k = wait_k; P.publish_k = publish_k; P.peer_counter = peers->counter; P.peer_error = peers->error;
   }
   return dispatch(P, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- replicas of the archive over NVLink
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
-  uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// "append #k of this rank is in every replica": one thread per peer publishes k into the peer's flag array.
-// Launched after the appending step kernel: its peer stores are complete when this kernel starts.
-__global__ void dreamzs_publish_kernel(dreamzs_peers pr, uint64_t k) {
-  const int q = threadIdx.x;
-  if (q < pr.world && q != pr.rank) {
-    __threadfence_system();
-    st_release_sys(pr.flags[q] + pr.rank, k);
-  }
-}
-// wait until every peer has published append #k (their rows are then in this rank's replica)
-__global__ void dreamzs_wait_kernel(dreamzs_peers pr, uint64_t k) {
-  const int q = threadIdx.x;
-  if (q < pr.world && q != pr.rank) {
-    const uint64_t *f = pr.flags[pr.rank] + q;
-    const uint64_t t0 = globaltimer_ns();
-    while (ld_acquire_sys(f) < k) {
-      if (globaltimer_ns() - t0 > DREAMZS_PEER_TIMEOUT_NS) { atomicExch(pr.error, 1); break; }
-      __nanosleep(200);
-    }
-  }
-}
-
 extern "C" int dreamzs_shared_alloc(int64_t bytes, void **dev_ptr, void *handle) {
   if (bytes <= 0 || !dev_ptr || !handle) return DREAMZS_E_BADARG;
   void *p = nullptr;
@@ -232,7 +203,6 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
   if (sharded && !hook && !(peers && peers->world > 1)) return DREAMZS_E_BADARG;   // other shards' rows need a transport
   const bool p2p = peers && peers->world > 1;
   const int64_t thin = cfg->history_thin, end = iter_begin + niter;
-  cudaStream_t s = (cudaStream_t)stream;
   dreamzs_trace w = *tr;
   int64_t t = iter_begin, nl = 0;
   bool waited = appends_done == 0;       // nothing of the peers to wait for before the first append
@@ -240,20 +210,17 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
     const int64_t nxt = ((t + thin - 1) / thin) * thin;          // first appending iteration >= t
     const int64_t n = (end < nxt + 1 ? end : nxt + 1) - t;
     w.trace_offset = tr->trace_offset + (t - iter_begin);
-    if (p2p && !waited) {
-      dreamzs_wait_kernel<<<1, 32, 0, s>>>(*peers, (uint64_t)appends_done);
-      waited = true;
-      ++nl;
-    }
-    int rc = step_impl(cfg, st, &w, t, (int32_t)n, archive_rows, p2p ? peers : nullptr, stream);
+    const bool appends = (t + n - 1) % thin == 0;
+    // with peers the launch itself waits for append #appends_done of the others (once) and publishes its own
+    int rc = step_impl(cfg, st, &w, t, (int32_t)n, archive_rows, p2p ? peers : nullptr,
+                       (p2p && !waited) ? (uint64_t)appends_done : 0, (p2p && appends) ? (uint64_t)(appends_done + 1) : 0, stream);
     if (rc != DREAMZS_OK) return rc;
+    waited = true;
     ++nl;
-    if ((t + n - 1) % thin == 0) {                               // record_history for every chain (Dream.py:919-938)
+    if (appends) {                                               // record_history for every chain (Dream.py:919-938)
       ++appends_done;
       if (p2p) {
-        dreamzs_publish_kernel<<<1, 32, 0, s>>>(*peers, (uint64_t)appends_done);
         waited = false;
-        ++nl;
       } else if (hook) {
         rc = hook(user, archive_rows, cfg->nchains_global);
         if (rc != DREAMZS_OK) return rc;
@@ -262,7 +229,6 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
     }
     t += n;
   }
-  if (cudaGetLastError() != cudaSuccess) return DREAMZS_E_LAUNCH;
   if (launches) *launches = nl;
   if (archive_rows_out) *archive_rows_out = archive_rows;
   return DREAMZS_OK;

@@ -105,6 +105,43 @@ __device__ __forceinline__ int gsum_int(int v, unsigned gmask) {
   return v;
 }
 
+// ---------------------------------------------------------------- replicas of the archive over NVLink (dreamzs_peers)
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// One thread: wait until every peer has published append #k (its rows are then in this rank's replica).
+__device__ __forceinline__ void peer_wait(const uint64_t *my_flags, int world, int rank, uint64_t k, int32_t *error) {
+  const uint64_t t0 = globaltimer_ns();
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) continue;
+    while (ld_acquire_sys(my_flags + q) < k) {
+      if (globaltimer_ns() - t0 > DREAMZS_PEER_TIMEOUT_NS) { atomicExch(error, 1); return; }
+      __nanosleep(100);
+    }
+  }
+}
+// The leader lane of a chain, after the chain's rows went to every replica and every storing lane executed
+// __threadfence_system(): count the chain; the last one publishes "append #k done" to every peer.
+__device__ __forceinline__ void peer_chain_appended(unsigned int *counter, unsigned int nchains, uint64_t *const *peer_flag,
+                                                    int npeers, uint64_t k) {
+  const unsigned int old = atomicAdd(counter, 1u);
+  if (old == nchains - 1u) {
+    atomicExch(counter, 0u);
+    __threadfence_system();
+    for (int q = 0; q < npeers; ++q) st_release_sys(peer_flag[q], k);
+  }
+}
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device): `cache` is a per-kernel array
 // indexed by device ordinal (the launchers keep it in a function-local static).
 template <typename K>

@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(GK_THREADS, 1) dreamzs_gauss_kernel(const Step
     return dc;
   };
 
+  if (has_chain && P.wait_k) {   // sharded archive: the peers' rows of the previous append must have landed
+    if (lane == 0) peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);
+    __syncwarp();
+  }
   if (has_chain) {
     if (own) {
       const double *xrow = P.st.X + (size_t)c_local * ld + i0;
@@ -403,6 +407,11 @@ __global__ void __launch_bounds__(GK_THREADS, 1) dreamzs_gauss_kernel(const Step
             *reinterpret_cast<double2 *>(zp + 2) = make_double2(x0[0][2], x0[0][3]);
           }
         }
+      }
+      if (P.publish_k && iter % P.cfg.history_thin == 0) {
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
       }
       if (lane == 0) {
         P.tr.trace_logp[(size_t)c_local * P.tr.trace_iters + trow] = last_like + last_prior;

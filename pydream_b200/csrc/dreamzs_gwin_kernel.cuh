@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
       cst[warp * 4 + 2] = P.st.last_like[c_local];
     }
   }
+  if (P.wait_k && tid == 32) peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);   // peers' rows have landed
   __syncthreads();
   if (tid == 0) {
     fence_proxy_async();
@@ -568,6 +569,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
               *reinterpret_cast<double2 *>(zp + 2) = make_double2(x0[2], x0[3]);
             }
           }
+        }
+        if (P.publish_k && P.gw_append && done + itb == P.niter - 1) {
+          __threadfence_system();
+          __syncwarp();
+          if (lane == 0) peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
         }
         if (lane == 0) {
           *lrow_ptr = last_like + last_prior;

@@ -503,6 +503,10 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
   for (int j = 0; j < P.cfg.ngamma; ++j) gp[j] = P.st.gamma_probs[j];
 
   const int64_t M = P.archive_rows;
+  if (P.wait_k) {   // sharded archive: the peers' rows of the previous append must have landed in this replica
+    if (c.g == 0) peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);
+    __syncwarp(c.gmask);
+  }
 #pragma unroll 1
   for (int it = 0; it < P.niter; ++it) {
     const int64_t iter = P.iter_begin + it;
@@ -601,6 +605,11 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
     if (iter % P.cfg.history_thin == 0) {
       store_row<G, R>(c, P.st.Z + (size_t)(M + c_global) * ld, x0);
       for (int pz = 0; pz < P.npeers; ++pz) store_row<G, R>(c, P.peer_Z[pz] + (size_t)(M + c_global) * ld, x0);   // replicas over NVLink
+      if (P.publish_k) {
+        __threadfence_system();
+        __syncwarp(c.gmask);
+        if (c.g == 0) peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
+      }
     }
     __syncwarp(c.gmask);
   }

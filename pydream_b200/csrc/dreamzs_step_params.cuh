@@ -19,6 +19,13 @@ struct StepParams {
   int32_t gw_nb;          // window kernel: iterations per batch
   int32_t npeers;         // other GPUs holding a replica of the archive (NVLink peer mappings)
   double *peer_Z[DREAMZS_MAX_PEERS];   // their Z, as mapped in this process
+  uint64_t *peer_flag[DREAMZS_MAX_PEERS];   // their flag word for this rank (flags[q] + rank)
+  const uint64_t *my_flags;   // this rank's flag array (one word per rank)
+  int32_t my_rank, world;
+  uint64_t wait_k;        // != 0: before touching the archive wait until every peer has published append #wait_k
+  uint64_t publish_k;     // != 0: this launch appends; when all local chains have, publish append #publish_k
+  unsigned int *peer_counter;   // chains of this launch that have appended (scratch, returns to 0)
+  int32_t *peer_error;
   long long *dbg;         // optional phase-timestamp buffer (dreamzs_debug_set_phase_buffer; profiling aid)
   int32_t gw_append;      // window kernel: the last iteration of the launch appends to the archive
   int32_t gw_refresh;     // window kernel: re-derive gauss_Y / gauss_Q from X at the start of the launch

@@ -26,7 +26,8 @@ from . import targets as T
 from .collectives import allgather_rows, allreduce_sum
 
 
-SHARED_HEADER = 4096      # bytes in front of a shared archive block: flags (8 x uint64) at 0, error word at 1024
+SHARED_HEADER = 4096      # bytes in front of a shared archive block: flags (8 x uint64) at 0, error word at 1024,
+                          # appended-chains counter at 2048
 
 
 class _DevicePtr:
@@ -254,6 +255,7 @@ class DreamEngine:
         for q, pq in enumerate(opened):
             pr.Z[q] = pq + SHARED_HEADER
             pr.flags[q] = pq
+        pr.counter = base.value + 2048
         pr.error = base.value + 1024
         self.peers = pr
         return block[SHARED_HEADER:].view(torch.float64).view(rows, self.ld)

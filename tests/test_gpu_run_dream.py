@@ -113,3 +113,36 @@ def test_converges_to_gaussian_target():
     x = np.concatenate([s[1500:] for s in sampled])
     assert np.all(np.abs(x.mean(axis=0)) < 0.1) and np.all(np.abs(x.std(axis=0) - 1) < 0.1)
     assert np.all(Gelman_Rubin(sampled) < 1.1)
+
+
+def test_streamed_chunks_equal_one_chunk():
+    """run_dream streams the samples to the host in chunks while sampling continues; the chunk size must not
+    change anything (odd chunk sizes, chunks that do not divide the run, a row stride with padding)."""
+    d = 10
+    rng = np.random.default_rng(5)
+    hist = rng.normal(size=(64, d))
+    like = targets.BimodalMixture.benchmark(d)
+    params = FlatParam(test_value=np.zeros(d))
+    kw = dict(niterations=57, nchains=7, start=[hist[c] for c in range(7)], start_random=False, history_file=hist,
+              verbose=False, save_history=False, seed=21, history_thin=4)
+    ref_s, ref_l = run_dream(params, like, stream_chunk=1000, **kw)
+    for chunk in (1, 7, 56):
+        s, l = run_dream(params, like, stream_chunk=chunk, **kw)
+        for c in range(7):
+            np.testing.assert_array_equal(s[c], ref_s[c])
+            np.testing.assert_array_equal(l[c], ref_l[c])
+    # adaptation during burn-in crosses chunk boundaries
+    params2, like2 = multidmodel()
+    kw2 = dict(niterations=45, nchains=5, verbose=False, save_history=False, seed=4, adapt_crossover=True, crossover_burnin=30)
+    a_s, a_l = run_dream(params2, like2, stream_chunk=1000, **kw2)
+    b_s, b_l = run_dream(params2, like2, stream_chunk=8, **kw2)
+    for c in range(5):
+        np.testing.assert_array_equal(a_s[c], b_s[c])
+        np.testing.assert_array_equal(a_l[c], b_l[c])
+
+
+def test_verbose_prints_acceptance(capsys):
+    params, like = multidmodel()
+    run_dream(params, like, niterations=30, nchains=3, verbose=True, nverbose=10, save_history=False, seed=1)
+    out = capsys.readouterr().out
+    assert 'acceptance rate' in out and 'Iteration:  20' in out
