@@ -133,7 +133,9 @@ def test_streamed_chunks_equal_one_chunk():
             np.testing.assert_array_equal(l[c], ref_l[c])
     # adaptation during burn-in crosses chunk boundaries
     params2, like2 = multidmodel()
-    kw2 = dict(niterations=45, nchains=5, verbose=False, save_history=False, seed=4, adapt_crossover=True, crossover_burnin=30)
+    hist2 = rng.normal(size=(40, 4)) * np.array([.13, 5, .9, 1.0]) + np.array([-6.6, 3, 1.0, -.12])
+    kw2 = dict(niterations=45, nchains=5, verbose=False, save_history=False, seed=4, adapt_crossover=True, crossover_burnin=30,
+               start=[hist2[c] for c in range(5)], start_random=False, history_file=hist2)
     a_s, a_l = run_dream(params2, like2, stream_chunk=1000, **kw2)
     b_s, b_l = run_dream(params2, like2, stream_chunk=8, **kw2)
     for c in range(5):
