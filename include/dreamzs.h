@@ -176,8 +176,9 @@ int dreamzs_shared_close(void *dev_ptr);
 int dreamzs_shared_free(void *dev_ptr);
 
 /* The chain loop of _sample_dream (pydream/core.py:103-122) for iterations that need no host decision between
- * them (no adaptation): iterations iter_begin .. iter_begin+niter-1 as one dreamzs_step launch per window, a
- * window ending at an iteration t with t % history_thin == 0.  tr->trace_offset is the trace row of
+ * them: iterations iter_begin .. iter_begin+niter-1 as one dreamzs_step launch per window, a window ending
+ * at an iteration t with t % history_thin == 0 (burn-in iterations with adaptation: one launch each, see
+ * dreamzs_adapt).  tr->trace_offset is the trace row of
  * iter_begin.  `appends_done` = number of appends made so far (archive_rows = seed rows + appends_done *
  * nchains_global).  Sharded runs keep the replicas of the archive identical either through `peers`
  * (NVLink peer stores, see dreamzs_peers) or, when peers is NULL, through `hook(user, first_row, nrows)`,
@@ -186,9 +187,32 @@ int dreamzs_shared_free(void *dev_ptr);
  * *launches (optional) receives the number of kernel launches, *archive_rows_out (optional) the archive
  * size after the run. */
 typedef int (*dreamzs_append_hook)(void *user, int64_t first_row, int64_t nrows);
+
+/* Burn-in adaptation inside the native loop (Dream.py:364-401): while adapt != NULL and t <= crossover_burnin
+ * every iteration is its own launch, followed -- for 10 < t < crossover_burnin and once more at
+ * t == crossover_burnin -- by the reduction stages dreamzs_adapt_colsum/colsq/jumps/finish below.  All
+ * pointers are device buffers of the caller: colsum[d], colsq[d], partial[2 nCR + 2 ngamma], workspace
+ * (dreamzs_adapt_workspace_bytes), x_entry[nchains_local x ld] (receives the states at entry), the
+ * accumulators ncr_updates/delta_m[nCR], ngamma_updates/delta_m_gamma[ngamma] and the probabilities the
+ * step reads (the same buffers as dreamzs_state.cr_probs / gamma_probs).  Needs dreamzs_trace.decisions.
+ * Sharded runs pass `reduce(user, buffer, count)`, called after colsum, colsq and jumps to sum the buffer
+ * over the ranks (stream-ordered, e.g. an NCCL all-reduce); NULL when all chains are local. */
+typedef int (*dreamzs_reduce_hook)(void *user, double *buffer, int64_t count);
+typedef struct dreamzs_adapt {
+  int32_t adapt_crossover, adapt_gamma;
+  int64_t crossover_burnin;
+  double *colsum, *colsq, *partial;
+  void *workspace;
+  double *x_entry;
+  double *ncr_updates, *delta_m, *cr_probs;
+  double *ngamma_updates, *delta_m_gamma, *gamma_probs;
+  dreamzs_reduce_hook reduce;
+  void *user;
+} dreamzs_adapt;
+
 int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                 int64_t iter_begin, int64_t niter, int64_t archive_rows, int64_t appends_done,
-                const dreamzs_peers *peers, dreamzs_append_hook hook, void *user,
+                const dreamzs_peers *peers, dreamzs_append_hook hook, void *user, const dreamzs_adapt *adapt,
                 void *stream, int64_t *launches, int64_t *archive_rows_out);
 
 /* sampled_params / log_ps leave the device (pydream/core.py:81-86 returns them to the caller): stream-ordered

@@ -54,6 +54,15 @@ class Peers(C.Structure):
 
 
 APPEND_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64)
+REDUCE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+
+
+class Adapt(C.Structure):
+    _fields_ = [('adapt_crossover', C.c_int32), ('adapt_gamma', C.c_int32), ('crossover_burnin', C.c_int64),
+                ('colsum', C.c_void_p), ('colsq', C.c_void_p), ('partial', C.c_void_p), ('workspace', C.c_void_p),
+                ('x_entry', C.c_void_p), ('ncr_updates', C.c_void_p), ('delta_m', C.c_void_p), ('cr_probs', C.c_void_p),
+                ('ngamma_updates', C.c_void_p), ('delta_m_gamma', C.c_void_p), ('gamma_probs', C.c_void_p),
+                ('reduce', REDUCE_HOOK), ('user', C.c_void_p)]
 
 
 class DreamzsError(RuntimeError):
@@ -78,8 +87,8 @@ def load():
         'dreamzs_abi_version': (C.c_int, []),
         'dreamzs_init_logp': (C.c_int, [cfgp, stp, vp]),
         'dreamzs_step': (C.c_int, [cfgp, stp, trp, i64, i32, i64, vp]),
-        'dreamzs_run': (C.c_int, [cfgp, stp, trp, i64, i64, i64, i64, C.POINTER(Peers), APPEND_HOOK, vp, vp, C.POINTER(i64),
-                                  C.POINTER(i64)]),
+        'dreamzs_run': (C.c_int, [cfgp, stp, trp, i64, i64, i64, i64, C.POINTER(Peers), APPEND_HOOK, vp, C.POINTER(Adapt), vp,
+                                  C.POINTER(i64), C.POINTER(i64)]),
         'dreamzs_shared_alloc': (C.c_int, [i64, C.POINTER(vp), vp]),
         'dreamzs_shared_open': (C.c_int, [vp, C.POINTER(vp)]),
         'dreamzs_shared_close': (C.c_int, [vp]),

@@ -10,36 +10,60 @@
 
 namespace dreamzs {
 
-constexpr int ADAPT_ROWS_PER_CTA = 256;
+constexpr int ADAPT_ROWS_PER_CTA = 64;
+constexpr int ADAPT_TX = 32, ADAPT_TY = 8;
 
-// stage A: partial[cta][i] = sum over the CTA's chains of f(X[c][i]);  f = x  or (x - mean)^2
-__global__ void adapt_col_partial(const double *X, int nchains, int d, int ld, const double *colsum, double inv_n_is_div,
-                                  int nglobal, double *partial) {
+// stage A: partial[cta][i] = sum over the CTA's chains of f(X[c][i]);  f = x  or (x - mean)^2.
+// threadIdx.x over dimensions (coalesced rows), threadIdx.y over the CTA's chains; fixed-order tree over y.
+__global__ void __launch_bounds__(ADAPT_TX * ADAPT_TY) adapt_col_partial(const double *X, int nchains, int d, int ld, const double *colsum,
+                                                                         double inv_n_is_div, int nglobal, double *partial) {
+  __shared__ double sh[ADAPT_TY][ADAPT_TX];
   const int c0 = blockIdx.x * ADAPT_ROWS_PER_CTA;
   const int c1 = min(nchains, c0 + ADAPT_ROWS_PER_CTA);
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+  for (int ib = 0; ib < d; ib += ADAPT_TX) {
+    const int i = ib + threadIdx.x;
     double acc = 0.0;
-    if (colsum) {
-      const double mean = colsum[i] / (double)nglobal;
-      for (int c = c0; c < c1; ++c) { const double t = X[(size_t)c * ld + i] - mean; acc += t * t; }
-    } else {
-      for (int c = c0; c < c1; ++c) acc += X[(size_t)c * ld + i];
+    if (i < d) {
+      if (colsum) {
+        const double mean = colsum[i] / (double)nglobal;
+#pragma unroll 4
+        for (int c = c0 + threadIdx.y; c < c1; c += ADAPT_TY) { const double t = X[(size_t)c * ld + i] - mean; acc += t * t; }
+      } else {
+#pragma unroll 4
+        for (int c = c0 + threadIdx.y; c < c1; c += ADAPT_TY) acc += X[(size_t)c * ld + i];
+      }
     }
-    partial[(size_t)blockIdx.x * d + i] = acc;
+    sh[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < d) {
+      double tot = 0.0;
+      for (int y = 0; y < ADAPT_TY; ++y) tot += sh[y][threadIdx.x];
+      partial[(size_t)blockIdx.x * d + i] = tot;
+    }
+    __syncthreads();
   }
 }
-// stage B: out[i] = sum_cta partial[cta][i]  (fixed order)
-__global__ void adapt_col_finish(const double *partial, int nctas, int d, double *out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d) return;
+// stage B: out[i] = sum_cta partial[cta][i]  (threadIdx.y over the CTAs' partials, fixed-order tree)
+constexpr int ADAPT_FY = 32;
+__global__ void __launch_bounds__(ADAPT_TX * ADAPT_FY) adapt_col_finish(const double *partial, int nctas, int d, double *out) {
+  __shared__ double sh[ADAPT_FY][ADAPT_TX];
+  const int i = blockIdx.x * ADAPT_TX + threadIdx.x;
   double acc = 0.0;
-  for (int b = 0; b < nctas; ++b) acc += partial[(size_t)b * d + i];
-  out[i] = acc;
+  if (i < d)
+    for (int b = threadIdx.y; b < nctas; b += ADAPT_FY) acc += partial[(size_t)b * d + i];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < d) {
+    double tot = 0.0;
+    for (int y = 0; y < ADAPT_FY; ++y) tot += sh[y][threadIdx.x];
+    out[i] = tot;
+  }
 }
 
 // one warp per chain: change_c = nan_to_num(sum_i ((x_new - x_old)/sd_i)^2) for both sd conventions
 __global__ void adapt_jump_kernel(const double *Xn, const double *Xo, int64_t ld_old, int nchains, int d, int ld,
-                                  const double *colsq, int nglobal, double *jump_cr, double *jump_g) {
+                                  const double *colsq, int nglobal, const uint32_t *dec, int64_t dec_stride, double *jump_cr,
+                                  double *jump_g, uint32_t *dec_packed) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= nchains) return;
   double a = 0.0, b = 0.0;
@@ -51,38 +75,62 @@ __global__ void adapt_jump_kernel(const double *Xn, const double *Xo, int64_t ld
     a += t0 * t0; b += t1 * t1;
   }
   a = gsum<32>(a, 0xffffffffu); b = gsum<32>(b, 0xffffffffu);
-  if (lane == 0) { jump_cr[warp] = nan_to_num(a); jump_g[warp] = nan_to_num(b); }
+  if (lane == 0) {
+    jump_cr[warp] = nan_to_num(a); jump_g[warp] = nan_to_num(b);
+    dec_packed[warp] = dec[(size_t)warp * dec_stride];   // this iteration's decision words, gathered for the reduction
+  }
 }
 
-// single CTA: per-index counts and sums over the local chains in a fixed tree order
-__global__ void adapt_reduce_kernel(const double *jump_cr, const double *jump_g, const uint32_t *dec, int64_t dec_stride,
-                                    int nchains, int nCR, int ngamma, int final_update, int adapt_cr, int adapt_g,
-                                    double *partial) {
-  __shared__ double sh[1024];
+// single CTA, ONE pass over the chains: per-index counts and sums (2 nCR + 2 ngamma outputs) accumulated per
+// thread, then reduced in a fixed order (warp butterfly, then the 32 warp results in order): deterministic.
+constexpr int ADAPT_MAXOUT = 2 * DREAMZS_MAX_NCR + 2 * DREAMZS_MAX_NGAMMA;
+__global__ void __launch_bounds__(256) adapt_reduce_kernel(const double *jump_cr, const double *jump_g, const uint32_t *dec,
+                                                            int64_t dec_stride, int nchains, int nCR, int ngamma, int final_update,
+                                                            int adapt_cr, int adapt_g, double *partial) {
+  __shared__ double sh[32][ADAPT_MAXOUT];
   const int nout = 2 * nCR + 2 * ngamma;
-  for (int o = 0; o < nout; ++o) {
-    const bool is_cr = o < 2 * nCR;
-    const int idx = is_cr ? o % nCR : (o - 2 * nCR) % ngamma;
-    const bool is_count = is_cr ? o < nCR : (o - 2 * nCR) < ngamma;
-    double acc = 0.0;
-    if ((is_cr && adapt_cr) || (!is_cr && adapt_g)) {
-      for (int c = threadIdx.x; c < nchains; c += blockDim.x) {
-        const uint32_t w = dec[(size_t)c * dec_stride];
-        const int snk = (w >> 1) & 1, gone = (w >> 18) & 1;
-        bool use; int m;
-        if (is_cr) { use = final_update || !gone; m = snk ? nCR - 1 : (int)((w >> 2) & 15); }
-        else { use = final_update || (!gone && !snk); m = (int)((w >> 6) & 15); }
-        if (use && m == idx) acc += is_count ? 1.0 : (is_cr ? jump_cr[c] : jump_g[c]);
-      }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[ADAPT_MAXOUT];
+#pragma unroll
+  for (int o = 0; o < ADAPT_MAXOUT; ++o) acc[o] = 0.0;
+  for (int c = threadIdx.x; c < nchains; c += blockDim.x) {
+    const uint32_t w = dec[(size_t)c * dec_stride];
+    const int snk = (w >> 1) & 1, gone = (w >> 18) & 1;
+    const bool use_cr = adapt_cr && (final_update || !gone);
+    const bool use_g = adapt_g && (final_update || (!gone && !snk));
+    const int mcr = snk ? nCR - 1 : (int)((w >> 2) & 15), mg = (int)((w >> 6) & 15);
+    const double jc = jump_cr[c], jg = jump_g[c];
+#pragma unroll
+    for (int m = 0; m < DREAMZS_MAX_NCR; ++m) {
+      const bool hit = use_cr && m == mcr;
+      acc[m] += hit ? 1.0 : 0.0;
+      acc[DREAMZS_MAX_NCR + m] += hit ? jc : 0.0;
     }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-      if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
-      __syncthreads();
+#pragma unroll
+    for (int m = 0; m < DREAMZS_MAX_NGAMMA; ++m) {
+      const bool hit = use_g && m == mg;
+      acc[2 * DREAMZS_MAX_NCR + m] += hit ? 1.0 : 0.0;
+      acc[2 * DREAMZS_MAX_NCR + DREAMZS_MAX_NGAMMA + m] += hit ? jg : 0.0;
     }
-    if (threadIdx.x == 0) partial[o] = sh[0];
-    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 0; o < ADAPT_MAXOUT; ++o) {
+    acc[o] = gsum<32>(acc[o], 0xffffffffu);
+    if (lane == 0) sh[warp][o] = acc[o];
+  }
+  __syncthreads();
+  if (threadIdx.x < nout) {
+    // output o of the packed layout [count_cr | sum_cr | count_g | sum_g] -> slot of the padded layout
+    const int o = threadIdx.x;
+    int slot;
+    if (o < nCR) slot = o;
+    else if (o < 2 * nCR) slot = DREAMZS_MAX_NCR + (o - nCR);
+    else if (o < 2 * nCR + ngamma) slot = 2 * DREAMZS_MAX_NCR + (o - 2 * nCR);
+    else slot = 2 * DREAMZS_MAX_NCR + DREAMZS_MAX_NGAMMA + (o - 2 * nCR - ngamma);
+    double tot = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int wv = 0; wv < nw; ++wv) tot += sh[wv][slot];
+    partial[o] = tot;
   }
 }
 
@@ -126,7 +174,7 @@ static int ok(void) { return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DR
 
 extern "C" int64_t dreamzs_adapt_workspace_bytes(const dreamzs_config *cfg) {
   if (!cfg) return DREAMZS_E_BADARG;
-  const int64_t a = (int64_t)(nctas_of(cfg) > 0 ? nctas_of(cfg) : 1) * cfg->ndim, b = 2 * (int64_t)cfg->nchains_local;
+  const int64_t a = (int64_t)(nctas_of(cfg) > 0 ? nctas_of(cfg) : 1) * cfg->ndim, b = 3 * (int64_t)cfg->nchains_local;
   return (int64_t)sizeof(double) * (a > b ? a : b) + 64;
 }
 
@@ -135,8 +183,9 @@ static int col_stage(const dreamzs_config *cfg, const double *X, const double *c
   cudaStream_t s = (cudaStream_t)stream;
   const int n = nctas_of(cfg);
   if (n == 0) { cudaMemsetAsync(out, 0, sizeof(double) * cfg->ndim, s); return ok(); }
-  adapt_col_partial<<<n, 128, 0, s>>>(X, cfg->nchains_local, cfg->ndim, cfg->ld, colsum, 0.0, cfg->nchains_global, (double *)ws);
-  adapt_col_finish<<<(cfg->ndim + 127) / 128, 128, 0, s>>>((const double *)ws, n, cfg->ndim, out);
+  adapt_col_partial<<<n, dim3(ADAPT_TX, ADAPT_TY), 0, s>>>(X, cfg->nchains_local, cfg->ndim, cfg->ld, colsum, 0.0, cfg->nchains_global,
+                                                          (double *)ws);
+  adapt_col_finish<<<(cfg->ndim + ADAPT_TX - 1) / ADAPT_TX, dim3(ADAPT_TX, ADAPT_FY), 0, s>>>((const double *)ws, n, cfg->ndim, out);
   return ok();
 }
 
@@ -156,9 +205,10 @@ extern "C" int dreamzs_adapt_jumps(const dreamzs_config *cfg, const double *X_ne
   cudaStream_t s = (cudaStream_t)stream;
   const int N = cfg->nchains_local;
   double *jc = (double *)workspace, *jg = jc + N;
+  uint32_t *dp = (uint32_t *)(jg + N);
   if (N > 0) adapt_jump_kernel<<<(N * 32 + 127) / 128, 128, 0, s>>>(X_new, x_old, ld_old, N, cfg->ndim, cfg->ld, colsq,
-                                                                      cfg->nchains_global, jc, jg);
-  adapt_reduce_kernel<<<1, 1024, 0, s>>>(jc, jg, decisions, dec_stride, N, cfg->nCR, cfg->ngamma, final_update,
+                                                                      cfg->nchains_global, decisions, dec_stride, jc, jg, dp);
+  adapt_reduce_kernel<<<1, 256, 0, s>>>(jc, jg, dp, 1, N, cfg->nCR, cfg->ngamma, final_update,
                                          adapt_crossover, adapt_gamma, partial);
   return ok();
 }

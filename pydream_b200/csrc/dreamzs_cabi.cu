@@ -194,8 +194,8 @@ extern "C" int dreamzs_shared_free(void *dev_ptr) {
 // _sample_dream's loop (pydream/core.py:103-122) for the steady state (no adaptation): one launch per window.
 extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                            int64_t iter_begin, int64_t niter, int64_t archive_rows, int64_t appends_done,
-                           const dreamzs_peers *peers, dreamzs_append_hook hook, void *user, void *stream,
-                           int64_t *launches, int64_t *archive_rows_out) {
+                           const dreamzs_peers *peers, dreamzs_append_hook hook, void *user, const dreamzs_adapt *adapt,
+                           void *stream, int64_t *launches, int64_t *archive_rows_out) {
   if (!cfg || niter < 0 || iter_begin < 0 || !tr || appends_done < 0) return DREAMZS_E_BADARG;
   if (cfg->history_thin < 1) return DREAMZS_E_BADARG;
   if (peers && (peers->world < 1 || peers->world > DREAMZS_MAX_PEERS || !peers->error)) return DREAMZS_E_BADARG;
@@ -206,9 +206,23 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
   dreamzs_trace w = *tr;
   int64_t t = iter_begin, nl = 0;
   bool waited = appends_done == 0;       // nothing of the peers to wait for before the first append
+  const bool adapting = adapt && (adapt->adapt_crossover || adapt->adapt_gamma);
+  if (adapting) {
+    if (!tr->decisions || !adapt->colsum || !adapt->colsq || !adapt->partial || !adapt->workspace || !adapt->x_entry ||
+        !adapt->cr_probs || !adapt->gamma_probs || (sharded && !adapt->reduce))
+      return DREAMZS_E_BADARG;
+    if (t <= adapt->crossover_burnin &&
+        cudaMemcpyAsync(adapt->x_entry, st->X, (size_t)cfg->nchains_local * cfg->ld * sizeof(double), cudaMemcpyDeviceToDevice,
+                        (cudaStream_t)stream) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return DREAMZS_E_LAUNCH;
+    }
+  }
   while (t < end) {
     const int64_t nxt = ((t + thin - 1) / thin) * thin;          // first appending iteration >= t
-    const int64_t n = (end < nxt + 1 ? end : nxt + 1) - t;
+    int64_t n = (end < nxt + 1 ? end : nxt + 1) - t;
+    const bool burn = adapting && t <= adapt->crossover_burnin;
+    if (burn) n = 1;
     w.trace_offset = tr->trace_offset + (t - iter_begin);
     const bool appends = (t + n - 1) % thin == 0;
     // with peers the launch itself waits for append #appends_done of the others (once) and publishes its own
@@ -226,6 +240,27 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
         if (rc != DREAMZS_OK) return rc;
       }
       archive_rows += cfg->nchains_global;
+    }
+    if (burn && ((10 < t && t < adapt->crossover_burnin) || t == adapt->crossover_burnin)) {
+      // one sweep of estimate_crossover_probabilities / estimate_gamma_level_probs (Dream.py:451-540)
+      const int64_t trow = w.trace_offset;
+      const double *x_old = trow == tr->trace_offset ? adapt->x_entry : tr->trace + (trow - 1) * cfg->ld;
+      const int64_t ld_old = trow == tr->trace_offset ? cfg->ld : tr->trace_iters * cfg->ld;
+      const int np = 2 * cfg->nCR + 2 * cfg->ngamma;
+      rc = dreamzs_adapt_colsum(cfg, st->X, adapt->colsum, adapt->workspace, stream);
+      if (rc == DREAMZS_OK && adapt->reduce) rc = adapt->reduce(adapt->user, adapt->colsum, cfg->ndim);
+      if (rc == DREAMZS_OK) rc = dreamzs_adapt_colsq(cfg, st->X, adapt->colsum, adapt->colsq, adapt->workspace, stream);
+      if (rc == DREAMZS_OK && adapt->reduce) rc = adapt->reduce(adapt->user, adapt->colsq, cfg->ndim);
+      if (rc == DREAMZS_OK)
+        rc = dreamzs_adapt_jumps(cfg, st->X, x_old, ld_old, tr->decisions + trow, tr->trace_iters, adapt->colsq,
+                                 t == adapt->crossover_burnin ? 1 : 0, adapt->adapt_crossover, adapt->adapt_gamma, adapt->partial,
+                                 adapt->workspace, stream);
+      if (rc == DREAMZS_OK && adapt->reduce) rc = adapt->reduce(adapt->user, adapt->partial, np);
+      if (rc == DREAMZS_OK)
+        rc = dreamzs_adapt_finish(cfg, adapt->partial, adapt->adapt_crossover, adapt->adapt_gamma, adapt->ncr_updates, adapt->delta_m,
+                                  adapt->cr_probs, adapt->ngamma_updates, adapt->delta_m_gamma, adapt->gamma_probs, stream);
+      if (rc != DREAMZS_OK) return rc;
+      nl += 7;
     }
     t += n;
   }

@@ -164,6 +164,7 @@ class DreamEngine:
         self.partial = torch.zeros(2 * nCR + 2 * gamma_levels, **f64)
         self.launches = 0
         self._hook = _cabi.APPEND_HOOK(self._append_hook)
+        self._reduce = _cabi.REDUCE_HOOK(self._reduce_hook)
         self._state()
         _cabi.check(self.lib.dreamzs_init_logp(C.byref(self.cfg), C.byref(self.st), self._stream()), 'dreamzs_init_logp')
         self.launches += 1
@@ -329,25 +330,26 @@ class DreamEngine:
         t = self.iter
         hook = self._hook if (self.world > 1 and self.peers is None) else _cabi.APPEND_HOOK()
         peers = C.byref(self.peers) if self.peers is not None else None
-
-        def native(t0, n):
-            tr.trace_offset = t0 - t_first
-            nl, rows = C.c_int64(0), C.c_int64(0)
-            rc = self.lib.dreamzs_run(cfg, st, C.byref(tr), t0, n, self.archive_rows, self.count // self.N, peers, hook,
-                                      None, stream, C.byref(nl), C.byref(rows))
-            _cabi.check(rc, 'dreamzs_run')
-            self.launches += int(nl.value)
-            self.count = int(rows.value) - self.nseed
-
+        adapt = None
         if adapting and t <= self.crossover_burnin:
-            self._x_entry = self.X.clone()
-            while t < end and t <= self.crossover_burnin:
-                native(t, 1)
-                if (10 < t < self.crossover_burnin) or t == self.crossover_burnin:
-                    self._adapt(trace, decisions, t - t_first, t == self.crossover_burnin)
-                t += 1
-        if t < end:
-            native(t, end - t)
+            # burn-in adaptation runs inside the native loop (dreamzs_adapt): one launch per iteration + reductions
+            p = lambda x: C.c_void_p(x.data_ptr())
+            if getattr(self, '_x_entry', None) is None:
+                self._x_entry = torch.empty_like(self.X)
+            self._adapt_ctx = _cabi.Adapt(
+                adapt_crossover=int(self.adapt_crossover), adapt_gamma=int(self.adapt_gamma), crossover_burnin=self.crossover_burnin,
+                colsum=p(self.colsum), colsq=p(self.colsq), partial=p(self.partial), workspace=p(self.workspace),
+                x_entry=p(self._x_entry), ncr_updates=p(self.ncr_updates), delta_m=p(self.delta_m), cr_probs=p(self.cr_probs),
+                ngamma_updates=p(self.ngamma_updates), delta_m_gamma=p(self.delta_m_gamma), gamma_probs=p(self.gamma_probs),
+                reduce=self._reduce if self.world > 1 else _cabi.REDUCE_HOOK(), user=None)
+            adapt = C.byref(self._adapt_ctx)
+        tr.trace_offset = 0
+        nl, rows = C.c_int64(0), C.c_int64(0)
+        rc = self.lib.dreamzs_run(cfg, st, C.byref(tr), t, end - t, self.archive_rows, self.count // self.N, peers, hook,
+                                  None, adapt, stream, C.byref(nl), C.byref(rows))
+        _cabi.check(rc, 'dreamzs_run')
+        self.launches += int(nl.value)
+        self.count = int(rows.value) - self.nseed
         self.iter = end
 
     def run_to_host(self, niter, out_params, out_logp, chunk_iters=256, on_chunk=None):
@@ -410,31 +412,18 @@ class DreamEngine:
             traceback.print_exc()
             return _cabi.E_LAUNCH
 
-    def _allreduce(self, t):
-        allreduce_sum(t, self.group)
-
-    def _adapt(self, trace, decisions, trow, final):
-        """One sweep of estimate_crossover_probabilities / estimate_gamma_level_probs (Dream.py:451-540)."""
-        lib, cfg, s = self.lib, C.byref(self.cfg), self._stream()
-        p = lambda t: C.c_void_p(t.data_ptr())
-        T_ = trace.shape[1]
-        if trow == 0:      # previous state is not in this call's trace: use the copy taken at run() entry
-            x_old, ld_old = p(self._x_entry), self.ld
-        else:
-            x_old, ld_old = C.c_void_p(trace.data_ptr() + (trow - 1) * self.ld * 8), T_ * self.ld
-        dec = C.c_void_p(decisions.data_ptr() + trow * 4)
-        _cabi.check(lib.dreamzs_adapt_colsum(cfg, p(self.X), p(self.colsum), p(self.workspace), s), 'dreamzs_adapt_colsum')
-        self._allreduce(self.colsum)
-        _cabi.check(lib.dreamzs_adapt_colsq(cfg, p(self.X), p(self.colsum), p(self.colsq), p(self.workspace), s), 'dreamzs_adapt_colsq')
-        self._allreduce(self.colsq)
-        _cabi.check(lib.dreamzs_adapt_jumps(cfg, p(self.X), x_old, ld_old, dec, T_, p(self.colsq), int(final),
-                                            int(self.adapt_crossover), int(self.adapt_gamma), p(self.partial),
-                                            p(self.workspace), s), 'dreamzs_adapt_jumps')
-        self._allreduce(self.partial)
-        _cabi.check(lib.dreamzs_adapt_finish(cfg, p(self.partial), int(self.adapt_crossover), int(self.adapt_gamma),
-                                             p(self.ncr_updates), p(self.delta_m), p(self.cr_probs), p(self.ngamma_updates),
-                                             p(self.delta_m_gamma), p(self.gamma_probs), s), 'dreamzs_adapt_finish')
-        self.launches += 7
+    def _reduce_hook(self, user, ptr, count):
+        """dreamzs_reduce_hook: sum one of the adaptation buffers over the ranks (enqueued on the current stream)."""
+        try:
+            for t in (self.colsum, self.colsq, self.partial):
+                if t.data_ptr() == ptr:
+                    allreduce_sum(t, self.group)
+                    return 0
+            return _cabi.E_BADARG
+        except Exception:      # never let an exception cross the C ABI
+            import traceback
+            traceback.print_exc()
+            return _cabi.E_LAUNCH
 
     # ------------------------------------------------------------------ diagnostics / export
     def gelman_rubin(self, trace):

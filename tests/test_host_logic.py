@@ -33,6 +33,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_cabi.State) == 16 * 8
     assert C.sizeof(_cabi.Trace) == 5 * 8
     assert C.sizeof(_cabi.Peers) == 8 + 8 * 8 + 8 * 8 + 8 + 8
+    assert C.sizeof(_cabi.Adapt) == 8 + 8 + 13 * 8
 
 
 def test_plan_segments():

@@ -1,6 +1,7 @@
 """Timing of the auxiliary kernels of the path: Gelman-Rubin (convergence.py:3-20) and one burn-in adaptation sweep
 (Dream.py:451-499) at the C5 shape, reported as achieved HBM GB/s of their algorithmic bytes."""
 import os, sys, time
+ONLY_ADAPT = '--adapt-only' in sys.argv
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,7 +18,7 @@ def timed(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 # Gelman-Rubin: N chains x T iterations x d (C5: 65536 x 1000 x 50 -> ld 52)
-for (N, T, d) in ((65536, 1000, 50), (1024, 10000, 100)):
+for (N, T, d) in (() if ONLY_ADAPT else ((65536, 1000, 50), (1024, 10000, 100))):
     ld = (d + 3) // 4 * 4
     trace = torch.randn((N, T, ld), dtype=torch.float64, device=dev)
     ms = timed(lambda: gelman_rubin_device(trace, d))
