@@ -148,6 +148,23 @@ int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state *st, void *
 int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                  int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream);
 
+/* Split step for likelihoods the caller evaluates (Model.total_logp calls the user's likelihood, pydream/model.py:30;
+ * target_kind DREAMZS_TARGET_EXTERNAL, multitry off).  One iteration of every local chain is
+ *   dreamzs_propose : decisions, archive gather, DE / snooker proposal, crossover, boundary handling, log prior
+ *                     (everything of Dream.astep up to the likelihood call, Dream.py:246-272); writes
+ *                     proposals[nchains_local x ld] and aux[nchains_local x 4] = (log prior of the proposal,
+ *                     snooker logp, |x - z|^2, gamma == 1 flag); no state changes
+ *   caller          : loglike[c] = log-likelihood of proposals[c] (any device computation on `stream`)
+ *   dreamzs_accept  : Metropolis accept, state / trace / decision updates, archive append when
+ *                     iter % history_thin == 0 (Dream.py:326-362); the random stream resumes where
+ *                     dreamzs_propose left it, so the pair consumes exactly the draws of the fused step.
+ * dreamzs_init_logp sets last_prior and leaves last_like = 0 for the caller to fill. */
+int dreamzs_propose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
+                    double *proposals, double *aux, void *stream);
+int dreamzs_accept(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter,
+                   int64_t archive_rows, const double *proposals, const double *aux, const double *loglike,
+                   void *stream);
+
 /* Replicas of the archive on the other GPUs of the box (pydream/Dream_shared_vars.py `history` is ONE shared
  * array in the reference; here every GPU holds a copy and the copies are kept identical over NVLink).
  * Z[q] / flags[q] are rank q's archive and flag array (DREAMZS_MAX_PEERS uint64, zero-initialised) as mapped

@@ -104,9 +104,9 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
 
     if not isinstance(likelihood, T.AnalyticTarget):
         raise NotImplementedError(
-            'pydream_b200 runs the whole step on the GPU and needs an analytic target from pydream_b200.targets '
-            '(CorrelatedGaussian, BimodalMixture, Banana, SumShift, Constant); arbitrary Python likelihoods are '
-            'not evaluated on the host (no CPU fallback)')
+            'pydream_b200 runs the whole step on the GPU and needs a target from pydream_b200.targets: an analytic one '
+            '(CorrelatedGaussian, BimodalMixture, Banana, SumShift, Constant) or TorchLikelihood(ndim, fn) wrapping a '
+            'batched device callable; arbitrary Python likelihoods are not evaluated on the host (no CPU fallback)')
     if likelihood.ndim != d:
         raise ValueError('target dimension %d != total parameter dimension %d' % (likelihood.ndim, d))
     prior_kind, prior_a, prior_b = _prior_arrays(parameters)

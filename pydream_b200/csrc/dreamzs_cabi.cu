@@ -36,6 +36,7 @@ static int table_doubles_of(const dreamzs_config *cfg) {
     case DREAMZS_TARGET_GAUSSIAN_DENSE: return 2 + cfg->ld * d;   // [log_F, 0, invC^T rows padded to ld]
     case DREAMZS_TARGET_MIXTURE: return 2 + 2 * d;
     case DREAMZS_TARGET_BANANA: return 2;
+    case DREAMZS_TARGET_EXTERNAL: return 1;
     default: return -1;
   }
 }
@@ -48,6 +49,7 @@ static int check_cfg(const dreamzs_config *cfg, const dreamzs_state *st) {
   if (cfg->nDEpairs < 1 || cfg->nDEpairs > DREAMZS_MAX_DEPAIRS) return DREAMZS_E_BADARG;
   if (cfg->multitry < 1 || 2 * cfg->multitry > DREAMZS_MAX_MULTITRY) return DREAMZS_E_BADARG;
   if (cfg->multitry == 2) return DREAMZS_E_UNSUPPORTED;   // broken in the reference too (Dream.py:867-868)
+  if (cfg->target_kind == DREAMZS_TARGET_EXTERNAL && cfg->multitry != 1) return DREAMZS_E_UNSUPPORTED;
   if (cfg->history_thin < 1) return DREAMZS_E_BADARG;
   if (!st->Z || !st->X || !st->last_prior || !st->last_like || !st->cr_probs || !st->gamma_probs || !st->gamma_table ||
       !st->target_table || !st->prior_kind || !st->prior_a || !st->prior_b || !st->mins || !st->maxs)
@@ -134,6 +136,7 @@ static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const d
                      void *stream) {
   int rc = check_cfg(cfg, st);
   if (rc != DREAMZS_OK) return rc;
+  if (cfg->target_kind == DREAMZS_TARGET_EXTERNAL) return DREAMZS_E_UNSUPPORTED;   // use dreamzs_propose / dreamzs_accept
   if (!tr || !tr->trace || !tr->trace_logp || niter < 0 || iter_begin < 0) return DREAMZS_E_BADARG;
   if (tr->trace_offset < 0 || tr->trace_offset + niter > tr->trace_iters) return DREAMZS_E_BADARG;
   if (archive_rows < 2 * cfg->nDEpairs || archive_rows > st->Z_capacity_rows) return DREAMZS_E_BADARG;
@@ -279,4 +282,38 @@ extern "C" int dreamzs_copy_d2h_2d(void *dst_host, int64_t dst_pitch_bytes, cons
                                           (size_t)height, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return DREAMZS_E_LAUNCH; }
   return DREAMZS_OK;
+}
+
+// ---------------------------------------------------------------- split step for caller-evaluated likelihoods
+// Model.total_logp calls the user's likelihood (pydream/model.py:30): with target_kind EXTERNAL one iteration is
+// dreamzs_propose -> caller evaluates log L of the proposals on the device -> dreamzs_accept.
+extern "C" int dreamzs_propose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
+                               double *proposals, double *aux, void *stream) {
+  int rc = check_cfg(cfg, st);
+  if (rc != DREAMZS_OK) return rc;
+  if (cfg->target_kind != DREAMZS_TARGET_EXTERNAL || !proposals || !aux || iter < 0) return DREAMZS_E_BADARG;
+  if (archive_rows < 2 * cfg->nDEpairs || archive_rows > st->Z_capacity_rows) return DREAMZS_E_BADARG;
+  if (cfg->nchains_local == 0) return DREAMZS_OK;
+  StepParams P{};
+  P.cfg = *cfg; P.st = *st; P.iter_begin = iter; P.niter = 1; P.archive_rows = archive_rows;
+  P.all_flat = all_flat_hint(cfg);
+  P.ext_phase = 1; P.ext_prop = proposals; P.ext_aux = aux;
+  return dispatch(P, (cudaStream_t)stream);
+}
+
+extern "C" int dreamzs_accept(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter,
+                              int64_t archive_rows, const double *proposals, const double *aux, const double *loglike,
+                              void *stream) {
+  int rc = check_cfg(cfg, st);
+  if (rc != DREAMZS_OK) return rc;
+  if (cfg->target_kind != DREAMZS_TARGET_EXTERNAL || !proposals || !aux || !loglike || iter < 0) return DREAMZS_E_BADARG;
+  if (!tr || !tr->trace || !tr->trace_logp || tr->trace_offset < 0 || tr->trace_offset + 1 > tr->trace_iters) return DREAMZS_E_BADARG;
+  if (archive_rows < 2 * cfg->nDEpairs || archive_rows > st->Z_capacity_rows) return DREAMZS_E_BADARG;
+  if (iter % cfg->history_thin == 0 && archive_rows + cfg->nchains_global > st->Z_capacity_rows) return DREAMZS_E_BADARG;
+  if (cfg->nchains_local == 0) return DREAMZS_OK;
+  StepParams P{};
+  P.cfg = *cfg; P.st = *st; P.tr = *tr; P.iter_begin = iter; P.niter = 1; P.archive_rows = archive_rows;
+  P.all_flat = all_flat_hint(cfg);
+  P.ext_phase = 2; P.ext_prop = const_cast<double *>(proposals); P.ext_aux = const_cast<double *>(aux); P.ext_like = loglike;
+  return dispatch(P, (cudaStream_t)stream);
 }

@@ -128,6 +128,7 @@ __device__ __forceinline__ void eval_logp(const Ctx<G, R> &c, const double (&x)[
         }
       like = -.5 * gsum<G>(acc, c.gmask);
     } break;
+    case DREAMZS_TARGET_EXTERNAL: like = 0.0; break;   // evaluated by the caller between dreamzs_propose and dreamzs_accept
     default: like = nan(""); break;
   }
 }
@@ -529,17 +530,44 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
     double new_prior, new_like;
     double q[R][4];
     if (k == 1) {
-      gamma_one = gen_eval_batch<G, R>(c, s, dc, 1, M, x0, 0, true, pri, lik, snk, D0);
-      const double q_prior = pri[0], q_like = lik[0];
+      double q_prior, q_like, snk0;
+      if (P.ext_phase == 2) {
+        // split step, second half: the proposal, its log prior and snooker terms come from dreamzs_propose, its
+        // log-likelihood from the caller; the random stream resumes where generate_proposal_points left it
+        const double *ax = P.ext_aux + (size_t)c_local * 4;
+        q_prior = ax[0]; snk0 = ax[1]; D0 = ax[2]; gamma_one = ax[3] != 0.0;
+        q_like = P.ext_like[c_local];
+        const double *prow = P.ext_prop + (size_t)c_local * ld;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i0 = c.dim0(r);
+          if (i0 < ld) {
+            const double2 a = *reinterpret_cast<const double2 *>(prow + i0), b = *reinterpret_cast<const double2 *>(prow + i0 + 2);
+            q[r][0] = a.x; q[r][1] = a.y; q[r][2] = b.x; q[r][3] = b.y;
+          } else q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0.0;
+        }
+        s.n_uscal = dc.run_snooker ? 1u : 0u;
+      } else {
+        gamma_one = gen_eval_batch<G, R>(c, s, dc, 1, M, x0, 0, true, pri, lik, snk, D0);
+        q_prior = pri[0]; q_like = lik[0]; snk0 = snk[0];
+        load_slot<G, R>(c, c.slots, q);
+        if (P.ext_phase == 1) {   // split step, first half: hand the proposal to the caller; no state changes
+          store_row<G, R>(c, P.ext_prop + (size_t)c_local * ld, q);
+          if (c.g == 0) {
+            double *ax = P.ext_aux + (size_t)c_local * 4;
+            ax[0] = q_prior; ax[1] = snk0; ax[2] = D0; ax[3] = gamma_one ? 1.0 : 0.0;
+          }
+          return;
+        }
+      }
       const double q_logp = 1.0 * q_like + q_prior;
       double mr;
       if (dc.run_snooker) {                                                            // Dream.py:326-332
         const double norm = sqrt(D0);
         const double cur = (norm != 0 ? log(norm) : 0.0) * (d - 1);
-        mr = nan_to_num((q_logp + snk[0]) - (last_logp + cur));
+        mr = nan_to_num((q_logp + snk0) - (last_logp + cur));
       } else mr = nan_to_num(q_logp) - nan_to_num(last_logp);                          // Dream.py:334
       if (isfinite(mr)) accepted = log(uniform_scalar(s)) < mr;                        // metrop_select, :980-998
-      load_slot<G, R>(c, c.slots, q);
       new_prior = q_prior; new_like = q_like;
     } else {
       double *rpri = pri + k, *rlik = lik + k, *rsnk = snk + k;   // MAX_MULTITRY >= 2k is not required: see host check

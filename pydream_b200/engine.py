@@ -122,7 +122,10 @@ class DreamEngine:
         # map each other's memory, else with an NCCL all-gather per append
         self.peers = None
         self._shared = None          # (own base pointer, [opened peer base pointers])
-        self._want_peers = bool(peer_archive) and self.world > 1 and self.world <= _cabi.MAX_PEERS
+        self.external = target.kind == T.TARGET_EXTERNAL     # likelihood evaluated by the caller: split step
+        if self.external and multitry != 1:
+            raise NotImplementedError('multi-try with a caller-evaluated likelihood (TorchLikelihood) is not implemented')
+        self._want_peers = bool(peer_archive) and self.world > 1 and self.world <= _cabi.MAX_PEERS and not self.external
         # the archive is sized once for `reserve_iters` iterations (it grows on demand beyond that)
         self._ensure_capacity(self.nseed + appends_in(0, int(reserve_iters), self.thin) * N)
         starts = np.asarray(starts, dtype=np.float64).reshape(N, d)
@@ -168,6 +171,10 @@ class DreamEngine:
         self._state()
         _cabi.check(self.lib.dreamzs_init_logp(C.byref(self.cfg), C.byref(self.st), self._stream()), 'dreamzs_init_logp')
         self.launches += 1
+        if self.external:
+            self._prop = torch.zeros((self.Nl, self.ld), **f64)
+            self._aux = torch.zeros((self.Nl, 4), **f64)
+            self.last_like.copy_(target.evaluate(self.X[:, :d].contiguous()))     # first-call logp, Dream.py:266-268
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -328,6 +335,9 @@ class DreamEngine:
         cfg, st = C.byref(self.cfg), C.byref(self.st)
         t_first, end = self.iter, self.iter + niter
         t = self.iter
+        if self.external:
+            self._advance_external(niter, trace, logp, decisions, tr)
+            return
         hook = self._hook if (self.world > 1 and self.peers is None) else _cabi.APPEND_HOOK()
         peers = C.byref(self.peers) if self.peers is not None else None
         adapt = None
@@ -351,6 +361,44 @@ class DreamEngine:
         self.launches += int(nl.value)
         self.count = int(rows.value) - self.nseed
         self.iter = end
+
+    def _advance_external(self, niter, trace, logp, decisions, tr):
+        """Split step for a caller-evaluated likelihood: per iteration dreamzs_propose -> target.evaluate ->
+        dreamzs_accept (+ the burn-in adaptation stages and the archive exchange of sharded runs)."""
+        lib, cfg, st, stream = self.lib, C.byref(self.cfg), C.byref(self.st), self._stream()
+        p = lambda x: C.c_void_p(x.data_ptr())
+        adapting = self.adapt_crossover or self.adapt_gamma
+        t_first = self.iter
+        if adapting and t_first <= self.crossover_burnin:
+            x_entry = self.X.clone()
+        for t in range(t_first, t_first + niter):
+            _cabi.check(lib.dreamzs_propose(cfg, st, t, self.archive_rows, p(self._prop), p(self._aux), stream), 'dreamzs_propose')
+            like = self.target.evaluate(self._prop[:, :self.d].contiguous() if self.ld != self.d else self._prop)
+            tr.trace_offset = t - t_first
+            _cabi.check(lib.dreamzs_accept(cfg, st, C.byref(tr), t, self.archive_rows, p(self._prop), p(self._aux), p(like), stream),
+                        'dreamzs_accept')
+            self.launches += 2
+            if adapting and ((10 < t < self.crossover_burnin) or t == self.crossover_burnin):
+                trow, T_ = t - t_first, trace.shape[1]
+                x_old, ld_old = (p(x_entry), self.ld) if trow == 0 else (C.c_void_p(trace.data_ptr() + (trow - 1) * self.ld * 8), T_ * self.ld)
+                dec = C.c_void_p(decisions.data_ptr() + trow * 4)
+                _cabi.check(lib.dreamzs_adapt_colsum(cfg, p(self.X), p(self.colsum), p(self.workspace), stream), 'dreamzs_adapt_colsum')
+                allreduce_sum(self.colsum, self.group)
+                _cabi.check(lib.dreamzs_adapt_colsq(cfg, p(self.X), p(self.colsum), p(self.colsq), p(self.workspace), stream), 'dreamzs_adapt_colsq')
+                allreduce_sum(self.colsq, self.group)
+                _cabi.check(lib.dreamzs_adapt_jumps(cfg, p(self.X), x_old, ld_old, dec, T_, p(self.colsq), int(t == self.crossover_burnin),
+                                                    int(self.adapt_crossover), int(self.adapt_gamma), p(self.partial), p(self.workspace), stream),
+                            'dreamzs_adapt_jumps')
+                allreduce_sum(self.partial, self.group)
+                _cabi.check(lib.dreamzs_adapt_finish(cfg, p(self.partial), int(self.adapt_crossover), int(self.adapt_gamma),
+                                                     p(self.ncr_updates), p(self.delta_m), p(self.cr_probs), p(self.ngamma_updates),
+                                                     p(self.delta_m_gamma), p(self.gamma_probs), stream), 'dreamzs_adapt_finish')
+                self.launches += 7
+            if t % self.thin == 0:       # record_history for every chain; sharded: gather the other ranks' rows
+                M = self.archive_rows
+                allgather_rows(self.Z[M:M + self.N], self.c0, self.Nl, self.group)
+                self.count += self.N
+        self.iter = t_first + niter
 
     def run_to_host(self, niter, out_params, out_logp, chunk_iters=256, on_chunk=None):
         """Run `niter` iterations and stream the samples to host memory while sampling continues.

@@ -147,3 +147,32 @@ class Banana(AnalyticTarget):
         if x.shape[0] > 2:
             ss = ss + np.sum(x[2:] * x[2:])
         return -.5 * ss
+
+
+class TorchLikelihood(AnalyticTarget):
+    """Escape hatch for likelihoods that are not one of the in-kernel analytic targets:
+    ``fn(points)`` receives a float64 CUDA tensor ``[n, ndim]`` (one proposal per chain) and returns the ``n``
+    log-likelihoods as a float64 CUDA tensor.  The step is then split into dreamzs_propose -> fn -> dreamzs_accept
+    (one launch pair per iteration, no window fusion); everything else of the step stays on the device.
+    As a host callable (``likelihood(param_vec) -> float``, pydream/model.py:30) it evaluates ``fn`` on one point."""
+    kind = TARGET_EXTERNAL
+
+    def __init__(self, ndim, fn):
+        self._ndim = int(ndim)
+        self.fn = fn
+
+    ndim = property(lambda self: self._ndim)
+
+    def table(self):
+        return np.array([0.0], dtype=np.float64)
+
+    def evaluate(self, points):
+        out = self.fn(points)
+        if out.dtype != points.dtype or out.shape != (points.shape[0],) or out.device != points.device:
+            raise ValueError('TorchLikelihood.fn must return a float64 tensor of shape [n] on the device of its input')
+        return out.contiguous()
+
+    def __call__(self, param_vec):
+        import torch
+        x = torch.as_tensor(np.asarray(param_vec, dtype=np.float64).reshape(1, -1), device='cuda')
+        return float(self.evaluate(x)[0].item())

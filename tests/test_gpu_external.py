@@ -1,0 +1,75 @@
+"""Split step for caller-evaluated likelihoods (dreamzs_propose -> torch callable -> dreamzs_accept; SURVEY.md 8(f)
+row 2): with a torch restatement of an analytic target it must reproduce the fused in-kernel step -- identical
+decisions and draws, log-posteriors within 1e-12 * max(1, |logp|)."""
+import numpy as np
+import pytest
+from scipy.stats import uniform
+
+from golden_util import logp_tol
+from pydream_b200 import targets
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(eng, T):
+    trace, logp, dec = eng.run(T)
+    d = eng.d
+    return (trace[:, :, :d].permute(1, 0, 2).contiguous().cpu().numpy(), logp.t().contiguous().cpu().numpy(),
+            dec.t().contiguous().cpu().numpy().astype(np.uint32))
+
+
+def _torch_mixture(tgt):
+    import torch
+    mu0 = torch.as_tensor(tgt.table()[2:2 + tgt.ndim], device='cuda')
+    mu1 = torch.as_tensor(tgt.table()[2 + tgt.ndim:2 + 2 * tgt.ndim], device='cuda')
+    lf0, lf1 = float(tgt.table()[0]), float(tgt.table()[1])
+
+    def fn(x):
+        l0 = -.5 * ((x - mu0) ** 2).sum(dim=1) + lf0
+        l1 = -.5 * ((x - mu1) ** 2).sum(dim=1) + lf1
+        mx = torch.maximum(l0, l1)
+        return torch.log(torch.exp(l0 - mx) + torch.exp(l1 - mx)) + mx
+    return fn
+
+
+@pytest.mark.parametrize('adapt', [False, True])
+def test_external_mixture_equals_fused(adapt):
+    from pydream_b200.engine import DreamEngine
+    d, N, T = 10, 96, 48
+    rng = np.random.default_rng(12)
+    hist = rng.normal(size=(2 * N + 7, d)) * 3
+    tgt = targets.BimodalMixture.benchmark(d)
+    kw = dict(seed=31, snooker=.2, history_thin=4, adapt_crossover=adapt, crossover_burnin=30 if adapt else 0)
+    a = _run(DreamEngine(d, N, hist, hist[:N], tgt, **kw), T)
+    ext = targets.TorchLikelihood(d, _torch_mixture(tgt))
+    eng = DreamEngine(d, N, hist, hist[:N], ext, **kw)
+    b = _run(eng, 17)
+    b2 = _run(eng, T - 17)          # a second call continues the same chains
+    b = tuple(np.concatenate([b[i], b2[i]], axis=0) for i in range(3))
+    np.testing.assert_array_equal(a[2], b[2])
+    assert np.all(np.abs(a[1] - b[1]) <= logp_tol(a[1])), (np.abs(a[1] - b[1]) / logp_tol(a[1])).max()
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=1e-13)
+
+
+def test_external_with_bounded_prior_and_run_dream():
+    """uniform prior + hard boundaries (reflection / redraw happen in dreamzs_propose), through run_dream."""
+    import torch
+    from pydream_b200.core import run_dream
+    from pydream_b200.parameters import SampledParam
+    lower, upper = np.array([-5., -9, 5, 3]), np.array([10., 2, 7, 8])
+    params = [SampledParam(uniform, loc=lower, scale=upper - lower)]
+    rng = np.random.default_rng(3)
+    hist = rng.uniform(lower, upper, size=(64, 4))
+    kw = dict(niterations=200, nchains=6, start=[hist[c] for c in range(6)], start_random=False, history_file=hist,
+              verbose=False, save_history=False, seed=9)
+    ref_s, ref_l = run_dream(params, targets.SumShift(4, 3.0), **kw)
+    ext = targets.TorchLikelihood(4, lambda x: (x + 3.0).sum(dim=1))
+    s, l = run_dream(params, ext, **kw)
+    for c in range(6):
+        np.testing.assert_allclose(s[c], ref_s[c], rtol=1e-12)
+        np.testing.assert_allclose(l[c], ref_l[c], rtol=1e-12)
+        assert np.all(s[c] >= lower) and np.all(s[c] <= upper)
+    # as a host callable (the reference's likelihood(param_vec) -> float contract)
+    assert abs(ext(np.array([1., 2, 3, 4])) - 22.0) < 1e-12
+    with pytest.raises(NotImplementedError):
+        run_dream(params, ext, multitry=5, **kw)
