@@ -451,7 +451,19 @@ __device__ __forceinline__ bool gen_eval_batch(const Ctx<G, R> &c, Stream &s, co
   return gamma_one;
 }
 
+// The multi-try path calls the batch generator twice (proposals, reference set): ONE out-of-line copy keeps the
+// kernel's instruction footprint down (the fused multi-try kernel is instruction-fetch bound: ncu no_instruction
+// stalls 3.5 warps per issue at d=10); the single-try path keeps the inlined copy, whose state stays in registers.
 template <int G, int R>
+__device__ __noinline__ bool gen_eval_batch_mt(const Ctx<G, R> &c, Stream &s, const Decisions &dc, int n, int64_t M,
+                                               const double (&ctr)[R][4], int slot0, bool one_slot, double *pri,
+                                               double *lik, double *snk, double &D0) {
+  return gen_eval_batch<G, R>(c, s, dc, n, M, ctr, slot0, one_slot, pri, lik, snk, D0);
+}
+
+// MT = the multi-try code is compiled in (a separate instantiation: its out-of-line batch generator takes the chain
+// state by reference, which would push the single-try kernel's registers into local memory as well)
+template <int G, int R, bool MT>
 __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
   extern __shared__ __align__(16) double smem[];
   const int d = P.cfg.ndim, ld = P.cfg.ld, k = P.cfg.multitry;
@@ -529,7 +541,7 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
     int sel = 0;
     double new_prior, new_like;
     double q[R][4];
-    if (k == 1) {
+    if (!MT || k == 1) {
       double q_prior, q_like, snk0;
       if (P.ext_phase == 2) {
         // split step, second half: the proposal, its log prior and snooker terms come from dreamzs_propose, its
@@ -569,10 +581,10 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
       } else mr = nan_to_num(q_logp) - nan_to_num(last_logp);                          // Dream.py:334
       if (isfinite(mr)) accepted = log(uniform_scalar(s)) < mr;                        // metrop_select, :980-998
       new_prior = q_prior; new_like = q_like;
-    } else {
+    } else if constexpr (MT) {
       double *rpri = pri + k, *rlik = lik + k, *rsnk = snk + k;   // MAX_MULTITRY >= 2k is not required: see host check
       for (int guard = 0;; ++guard) {                                                  // Dream.py:278-289
-        gamma_one = gen_eval_batch<G, R>(c, s, dc, k, M, x0, 0, false, pri, lik, snk, D0);
+        gamma_one = gen_eval_batch_mt<G, R>(c, s, dc, k, M, x0, 0, false, pri, lik, snk, D0);
         bool anyfinite = false;
         for (int p = 0; p < k; ++p) anyfinite |= isfinite(1.0 * lik[p] + pri[p]);
         if (anyfinite || guard >= 1000) break;
@@ -586,7 +598,7 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
       sel = multinomial_index(s, prob, k);
       load_slot<G, R>(c, c.slots + (size_t)sel * ld, q);
       // reference set around the selected proposal, Dream.py:295-303
-      gamma_one = gen_eval_batch<G, R>(c, s, dc, k - 1, M, q, k, true, rpri, rlik, rsnk, D0);
+      gamma_one = gen_eval_batch_mt<G, R>(c, s, dc, k - 1, M, q, k, true, rpri, rlik, rsnk, D0);
       double tp[DREAMZS_MAX_MULTITRY], trf[DREAMZS_MAX_MULTITRY];
       double m2 = -INFINITY;
       for (int p = 0; p < k; ++p) {
@@ -651,10 +663,10 @@ template <int G, int R>
 int launch_step(const StepParams &P, int threads, size_t smem, cudaStream_t stream) {
   const int chains_per_cta = (threads / 32) * (32 / G);
   const int grid = (P.cfg.nchains_local + chains_per_cta - 1) / chains_per_cta;
-  auto kern = dreamzs_step_kernel<G, R>;
+  auto kern = P.cfg.multitry > 1 ? dreamzs_step_kernel<G, R, true> : dreamzs_step_kernel<G, R, false>;
   if (smem > 48 * 1024) {
-    static size_t smem_set[64] = {0};
-    if (ensure_dynamic_smem(kern, smem, smem_set) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
+    static size_t smem_set[2][64] = {{0}};     // one cache per instantiation (single-try, multi-try)
+    if (ensure_dynamic_smem(kern, smem, smem_set[P.cfg.multitry > 1 ? 1 : 0]) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
   }
   kern<<<grid, threads, smem, stream>>>(P);
   return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;
