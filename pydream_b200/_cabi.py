@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libdreamzs.so')
+LIB_PATH = os.environ.get('DREAMZS_LIB') or os.path.join(HERE, 'libdreamzs.so')   # DREAMZS_LIB: A/B testing of builds
 
 ABI_VERSION = 2
 OK, E_BADARG, E_LAUNCH, E_UNSUPPORTED = 0, -1, -2, -3
