@@ -16,7 +16,7 @@ constexpr int ADAPT_TX = 32, ADAPT_TY = 8;
 // stage A: partial[cta][i] = sum over the CTA's chains of f(X[c][i]);  f = x  or (x - mean)^2.
 // threadIdx.x over dimensions (coalesced rows), threadIdx.y over the CTA's chains; fixed-order tree over y.
 __global__ void __launch_bounds__(ADAPT_TX * ADAPT_TY) adapt_col_partial(const double *X, int nchains, int d, int ld, const double *colsum,
-                                                                         double inv_n_is_div, int nglobal, double *partial) {
+                                                                         int nglobal, double *partial) {
   __shared__ double sh[ADAPT_TY][ADAPT_TX];
   const int c0 = blockIdx.x * ADAPT_ROWS_PER_CTA;
   const int c1 = min(nchains, c0 + ADAPT_ROWS_PER_CTA);
@@ -183,7 +183,7 @@ static int col_stage(const dreamzs_config *cfg, const double *X, const double *c
   cudaStream_t s = (cudaStream_t)stream;
   const int n = nctas_of(cfg);
   if (n == 0) { cudaMemsetAsync(out, 0, sizeof(double) * cfg->ndim, s); return ok(); }
-  adapt_col_partial<<<n, dim3(ADAPT_TX, ADAPT_TY), 0, s>>>(X, cfg->nchains_local, cfg->ndim, cfg->ld, colsum, 0.0, cfg->nchains_global,
+  adapt_col_partial<<<n, dim3(ADAPT_TX, ADAPT_TY), 0, s>>>(X, cfg->nchains_local, cfg->ndim, cfg->ld, colsum, cfg->nchains_global,
                                                           (double *)ws);
   adapt_col_finish<<<(cfg->ndim + ADAPT_TX - 1) / ADAPT_TX, dim3(ADAPT_TX, ADAPT_FY), 0, s>>>((const double *)ws, n, cfg->ndim, out);
   return ok();

@@ -178,7 +178,6 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
       //      0-5: snooker, CR, gamma level, gamma unity (Dream.py:542-599, 615), first two np.random.uniform()
       //      (snooker gamma :618 / Metropolis :993); 6-8: random.sample calls 0-2 (sample_from_history, :646-668)
       const int sk = min(lane / 10, GW_MAXCOLW - 1), kind = lane - 10 * (lane / 10);
-      int snk_k[GW_MAXCOLW];
       {
         const int cl = gw + GW_GWARPS * sk;
         const int ch = cl / NB, itb = cl - ch * NB;
@@ -212,8 +211,6 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
         const int snk = (s0 != 0u) && __shfl_sync(0xffffffffu, idx, base) == 0;
         const int cr_s = __shfl_sync(0xffffffffu, idx, base + 1), lvl_s = __shfl_sync(0xffffffffu, idx, base + 2);
         const int unity_s = __shfl_sync(0xffffffffu, idx, base + 3);
-#pragma unroll
-        for (int k = 0; k < GW_MAXCOLW; ++k) snk_k[k] = __shfl_sync(0xffffffffu, snk, 10 * k);
         const int col = gbase + cl;
         if (ok) {
           // meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set in V), 10 "not unity"
@@ -312,7 +309,6 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
           }
         }
       }
-      (void)snk_k;
       if (do_refresh && gw < gch && own) {   // refresh column of chain gw: x
         double *ws = Wc + (size_t)(ncol + gfirst + gw) * ld + i0;
         *reinterpret_cast<double2 *>(ws) = *reinterpret_cast<const double2 *>(Xs + (gfirst + gw) * ld + i0);

@@ -72,7 +72,8 @@ def appends_in(iter_begin, niter, thin):
 
 
 def plan_segments(iter_begin, niter, thin, single_until):
-    """Split [iter_begin, iter_begin+niter) into launches: a launch ends at an appending iteration
+    """The launch schedule of the native loop (dreamzs_run in csrc/dreamzs_cabi.cu), restated for tests and tools:
+    [iter_begin, iter_begin+niter) is split into launches; a launch ends at an appending iteration
     (t % thin == 0) and iterations t <= single_until run one per launch (burn-in adaptation)."""
     segs = []
     t, end = iter_begin, iter_begin + niter
@@ -88,6 +89,16 @@ def plan_segments(iter_begin, niter, thin, single_until):
 
 
 class DreamEngine:
+    """Device state + launch schedule of one MT-DREAM(ZS) run (the GPU stand-in for the reference's pool of chain
+    processes and its shared-memory namespace, pydream/core.py:250-327).
+
+    history [nseed, ndim] seeds the archive, starts [nchains, ndim] are the chains' first states, `target` is one of
+    pydream_b200.targets.  Keyword options carry the names and defaults of Dream.__init__ (pydream/Dream.py:63-67);
+    `group` shards the chains over a torch.distributed process group (this rank owns a contiguous block),
+    `reserve_iters` sizes the archive once for that many iterations, `peer_archive` selects NVLink peer stores
+    (default) or the NCCL all-gather for keeping the archive replicas identical.  `run(n)` advances all chains by n
+    iterations and returns device tensors; `run_to_host` streams the samples to pinned host memory meanwhile."""
+
     def __init__(self, ndim, nchains, history, starts, target, prior_kind=None, prior_a=None, prior_b=None, seed=0,
                  nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
                  history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,

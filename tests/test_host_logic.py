@@ -130,3 +130,48 @@ def test_targets_match_reference_example_formulas():
     mix = targets.BimodalMixture.benchmark(10)
     x = np.full(10, 5.0)
     assert np.isclose(mix(x), np.log(np.exp(-9.5949) + np.exp(-.5 * 1000 - 10.2880)))
+
+
+def test_c_abi_argument_checks_without_a_gpu():
+    """Entry points validate their arguments before touching the device: negative status codes, no exceptions."""
+    import ctypes as C
+    lib = _cabi.load()
+    cfg = _cabi.Config(abi_version=_cabi.ABI_VERSION, ndim=4, ld=4, nchains_global=8, chain_begin=0, nchains_local=8, nCR=3,
+                       ngamma=1, nDEpairs=1, multitry=1, hardboundaries=1, history_thin=10, target_kind=0, flags=0,
+                       snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12, seed=1)
+    st, tr = _cabi.State(), _cabi.Trace()
+    null_hook, null_adapt = _cabi.APPEND_HOOK(), None
+    # null state pointers
+    assert lib.dreamzs_step(C.byref(cfg), C.byref(st), C.byref(tr), 0, 1, 16, None) == _cabi.E_BADARG
+    assert lib.dreamzs_init_logp(C.byref(cfg), C.byref(st), None) == _cabi.E_BADARG
+    # wrong ABI version
+    bad = _cabi.Config.from_buffer_copy(cfg)
+    bad.abi_version = _cabi.ABI_VERSION + 1
+    assert lib.dreamzs_step(C.byref(bad), C.byref(st), C.byref(tr), 0, 1, 16, None) == _cabi.E_BADARG
+    # the native loop: negative counts, a sharded run without any transport for the other shards' rows
+    assert lib.dreamzs_run(C.byref(cfg), C.byref(st), C.byref(tr), 0, -1, 16, 0, None, null_hook, None, null_adapt, None,
+                           None, None) == _cabi.E_BADARG
+    shard = _cabi.Config.from_buffer_copy(cfg)
+    shard.nchains_local = 4
+    assert lib.dreamzs_run(C.byref(shard), C.byref(st), C.byref(tr), 0, 5, 16, 0, None, null_hook, None, null_adapt, None,
+                           None, None) == _cabi.E_BADARG
+    # zero iterations is a no-op that reports the unchanged archive size
+    rows, nl = C.c_int64(-1), C.c_int64(-1)
+    assert lib.dreamzs_run(C.byref(cfg), C.byref(st), C.byref(tr), 3, 0, 16, 0, None, null_hook, None, null_adapt, None,
+                           C.byref(nl), C.byref(rows)) == _cabi.OK
+    assert rows.value == 16 and nl.value == 0
+    # pitched copy, split step, shared allocations
+    assert lib.dreamzs_copy_d2h_2d(None, 8, None, 8, 8, 1, None) == _cabi.E_BADARG
+    assert lib.dreamzs_propose(C.byref(cfg), C.byref(st), 0, 16, None, None, None) == _cabi.E_BADARG
+    assert lib.dreamzs_accept(C.byref(cfg), C.byref(st), C.byref(tr), 0, 16, None, None, None, None) == _cabi.E_BADARG
+    assert lib.dreamzs_shared_alloc(0, None, None) == _cabi.E_BADARG
+    assert lib.dreamzs_gr_finish(None, None, 1, 1, 1, None, None) == _cabi.E_BADARG
+
+
+def test_appends_in_matches_the_schedule():
+    from pydream_b200.engine import plan_segments, appends_in
+    for t0, n, thin in ((0, 25, 10), (1, 9, 10), (7, 40, 3), (5, 0, 4), (10, 1, 10), (11, 9, 10)):
+        segs = plan_segments(t0, n, thin, -1)
+        assert sum(m for _, m in segs) == n
+        assert sum(1 for t, m in segs if (t + m - 1) % thin == 0) == appends_in(t0, n, thin)
+        assert all((t + i) % thin != 0 for t, m in segs for i in range(m - 1))      # only a launch's last iteration appends
