@@ -149,18 +149,26 @@ int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dream
                  int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream);
 
 /* Split step for likelihoods the caller evaluates (Model.total_logp calls the user's likelihood, pydream/model.py:30;
- * target_kind DREAMZS_TARGET_EXTERNAL, multitry off).  One iteration of every local chain is
+ * target_kind DREAMZS_TARGET_EXTERNAL).  Without multi-try one iteration of every local chain is
  *   dreamzs_propose : decisions, archive gather, DE / snooker proposal, crossover, boundary handling, log prior
  *                     (everything of Dream.astep up to the likelihood call, Dream.py:246-272); writes
  *                     proposals[nchains_local x ld] and aux[nchains_local x 4] = (log prior of the proposal,
  *                     snooker logp, |x - z|^2, gamma == 1 flag); no state changes
  *   caller          : loglike[c] = log-likelihood of proposals[c] (any device computation on `stream`)
  *   dreamzs_accept  : Metropolis accept, state / trace / decision updates, archive append when
- *                     iter % history_thin == 0 (Dream.py:326-362); the random stream resumes where
- *                     dreamzs_propose left it, so the pair consumes exactly the draws of the fused step.
- * dreamzs_init_logp sets last_prior and leaves last_like = 0 for the caller to fill. */
+ *                     iter % history_thin == 0 (Dream.py:326-362).
+ * With multitry = k > 1 (Dream.py:275-323) a chain has 2k-1 points: proposals[nchains_local x (2k-1) x ld],
+ * loglike[nchains_local x (2k-1)], aux[nchains_local x (4k+2)], and the iteration is
+ *   dreamzs_propose -> caller fills loglike[:, 0:k] -> dreamzs_select (mt_choose_proposal_pt, then the k-1 reference
+ *   points around the selected proposal go to proposals[:, k:2k-1]) -> caller fills loglike[:, k:2k-1] ->
+ *   dreamzs_accept.  The regenerate loop for a batch without any finite log-posterior (Dream.py:282-289) would need
+ *   new draws and is not split: dreamzs_select sets *error (device int32) to 1 instead.
+ * The random stream resumes in each phase where the previous one left it, so the phases consume exactly the draws
+ * of the fused step.  dreamzs_init_logp sets last_prior and leaves last_like = 0 for the caller to fill. */
 int dreamzs_propose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
                     double *proposals, double *aux, void *stream);
+int dreamzs_select(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
+                   double *proposals, double *aux, const double *loglike, int32_t *error, void *stream);
 int dreamzs_accept(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter,
                    int64_t archive_rows, const double *proposals, const double *aux, const double *loglike,
                    void *stream);

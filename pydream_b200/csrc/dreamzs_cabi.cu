@@ -49,7 +49,6 @@ static int check_cfg(const dreamzs_config *cfg, const dreamzs_state *st) {
   if (cfg->nDEpairs < 1 || cfg->nDEpairs > DREAMZS_MAX_DEPAIRS) return DREAMZS_E_BADARG;
   if (cfg->multitry < 1 || 2 * cfg->multitry > DREAMZS_MAX_MULTITRY) return DREAMZS_E_BADARG;
   if (cfg->multitry == 2) return DREAMZS_E_UNSUPPORTED;   // broken in the reference too (Dream.py:867-868)
-  if (cfg->target_kind == DREAMZS_TARGET_EXTERNAL && cfg->multitry != 1) return DREAMZS_E_UNSUPPORTED;
   if (cfg->history_thin < 1) return DREAMZS_E_BADARG;
   if (!st->Z || !st->X || !st->last_prior || !st->last_like || !st->cr_probs || !st->gamma_probs || !st->gamma_table ||
       !st->target_table || !st->prior_kind || !st->prior_a || !st->prior_b || !st->mins || !st->maxs)
@@ -70,7 +69,7 @@ static int dispatch(StepParams &P, cudaStream_t stream) {
   const int chunks = cfg.ld / 4;
   P.table_doubles = table_doubles_of(&cfg);
   if (P.table_doubles < 0) return DREAMZS_E_UNSUPPORTED;
-  P.nslots = cfg.multitry == 1 ? 1 : cfg.multitry + 1;
+  P.nslots = cfg.multitry == 1 ? 1 : (P.ext_phase ? 2 * cfg.multitry - 1 : cfg.multitry + 1);
   // dense Gaussian, flat priors, one DE pair, no multi-try, carried y = invC x: window kernel (dreamzs_gwin_kernel.cuh)
   if (gwin_eligible(P)) {
     if (P.init_only) return DREAMZS_OK;   // handled by the caller (generic evaluation + dreamzs_launch_gauss_refresh)
@@ -287,12 +286,19 @@ extern "C" int dreamzs_copy_d2h_2d(void *dst_host, int64_t dst_pitch_bytes, cons
 // ---------------------------------------------------------------- split step for caller-evaluated likelihoods
 // Model.total_logp calls the user's likelihood (pydream/model.py:30): with target_kind EXTERNAL one iteration is
 // dreamzs_propose -> caller evaluates log L of the proposals on the device -> dreamzs_accept.
-extern "C" int dreamzs_propose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
-                               double *proposals, double *aux, void *stream) {
+static int ext_common(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows, const double *proposals,
+                      const double *aux) {
   int rc = check_cfg(cfg, st);
   if (rc != DREAMZS_OK) return rc;
   if (cfg->target_kind != DREAMZS_TARGET_EXTERNAL || !proposals || !aux || iter < 0) return DREAMZS_E_BADARG;
   if (archive_rows < 2 * cfg->nDEpairs || archive_rows > st->Z_capacity_rows) return DREAMZS_E_BADARG;
+  return DREAMZS_OK;
+}
+
+extern "C" int dreamzs_propose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
+                               double *proposals, double *aux, void *stream) {
+  int rc = ext_common(cfg, st, iter, archive_rows, proposals, aux);
+  if (rc != DREAMZS_OK) return rc;
   if (cfg->nchains_local == 0) return DREAMZS_OK;
   StepParams P{};
   P.cfg = *cfg; P.st = *st; P.iter_begin = iter; P.niter = 1; P.archive_rows = archive_rows;
@@ -301,19 +307,32 @@ extern "C" int dreamzs_propose(const dreamzs_config *cfg, const dreamzs_state *s
   return dispatch(P, (cudaStream_t)stream);
 }
 
+extern "C" int dreamzs_select(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
+                              double *proposals, double *aux, const double *loglike, int32_t *error, void *stream) {
+  int rc = ext_common(cfg, st, iter, archive_rows, proposals, aux);
+  if (rc != DREAMZS_OK) return rc;
+  if (cfg->multitry < 2 || !loglike || !error) return DREAMZS_E_BADARG;
+  if (cfg->nchains_local == 0) return DREAMZS_OK;
+  StepParams P{};
+  P.cfg = *cfg; P.st = *st; P.iter_begin = iter; P.niter = 1; P.archive_rows = archive_rows;
+  P.all_flat = all_flat_hint(cfg);
+  P.ext_phase = 2; P.ext_prop = proposals; P.ext_aux = aux; P.ext_like = loglike; P.ext_error = error;
+  return dispatch(P, (cudaStream_t)stream);
+}
+
 extern "C" int dreamzs_accept(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter,
                               int64_t archive_rows, const double *proposals, const double *aux, const double *loglike,
                               void *stream) {
-  int rc = check_cfg(cfg, st);
+  int rc = ext_common(cfg, st, iter, archive_rows, proposals, aux);
   if (rc != DREAMZS_OK) return rc;
-  if (cfg->target_kind != DREAMZS_TARGET_EXTERNAL || !proposals || !aux || !loglike || iter < 0) return DREAMZS_E_BADARG;
+  if (!loglike) return DREAMZS_E_BADARG;
   if (!tr || !tr->trace || !tr->trace_logp || tr->trace_offset < 0 || tr->trace_offset + 1 > tr->trace_iters) return DREAMZS_E_BADARG;
-  if (archive_rows < 2 * cfg->nDEpairs || archive_rows > st->Z_capacity_rows) return DREAMZS_E_BADARG;
   if (iter % cfg->history_thin == 0 && archive_rows + cfg->nchains_global > st->Z_capacity_rows) return DREAMZS_E_BADARG;
   if (cfg->nchains_local == 0) return DREAMZS_OK;
   StepParams P{};
   P.cfg = *cfg; P.st = *st; P.tr = *tr; P.iter_begin = iter; P.niter = 1; P.archive_rows = archive_rows;
   P.all_flat = all_flat_hint(cfg);
-  P.ext_phase = 2; P.ext_prop = const_cast<double *>(proposals); P.ext_aux = const_cast<double *>(aux); P.ext_like = loglike;
+  P.ext_phase = cfg->multitry > 1 ? 3 : 2;
+  P.ext_prop = const_cast<double *>(proposals); P.ext_aux = const_cast<double *>(aux); P.ext_like = loglike;
   return dispatch(P, (cudaStream_t)stream);
 }

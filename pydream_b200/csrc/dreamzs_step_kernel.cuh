@@ -373,6 +373,13 @@ __device__ __forceinline__ void snooker_point(const Ctx<G, R> &c, Stream &s, con
   Dout = D;
 }
 
+// The call numbers a batch of n points consumes (the bookkeeping at the end of gen_eval_batch), without the rand()
+// redraws of the boundary handling, which are data dependent and carried separately.
+__device__ __forceinline__ void advance_batch_counters(Stream &s, const Decisions &dc, int n) {
+  if (dc.run_snooker) { s.n_multinomial += 1; s.n_uscal += 1; s.n_sample += 3 * n; }
+  else { s.n_sample += n; s.n_normal += n; s.n_uvec += 2 * n; s.n_multinomial += n; }
+}
+
 template <int G, int R>
 __device__ __forceinline__ void store_slot(const Ctx<G, R> &c, double *slot, const double (&x)[R][4]) {
 #pragma unroll
@@ -583,22 +590,95 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
       new_prior = q_prior; new_like = q_like;
     } else if constexpr (MT) {
       double *rpri = pri + k, *rlik = lik + k, *rsnk = snk + k;   // MAX_MULTITRY >= 2k is not required: see host check
-      for (int guard = 0;; ++guard) {                                                  // Dream.py:278-289
-        gamma_one = gen_eval_batch_mt<G, R>(c, s, dc, k, M, x0, 0, false, pri, lik, snk, D0);
-        bool anyfinite = false;
-        for (int p = 0; p < k; ++p) anyfinite |= isfinite(1.0 * lik[p] + pri[p]);
-        if (anyfinite || guard >= 1000) break;
+      // Split step with a caller-evaluated likelihood (ext_phase 1 / 2 / 3 = propose / select / accept): the
+      // 2k-1 points live in ext_prop [chain][2k-1][ld] (proposals first, then the reference set), their
+      // log-likelihoods in ext_like [chain][2k-1], and the scalars the next phase needs in ext_aux [chain][4k+2]:
+      //   [0,k) log prior, [k,2k) snooker logp of the proposals, 2k: rand() calls made so far, 2k+1: selected index,
+      //   [2k+2,3k+1) / [3k+1,4k) the same of the reference points, 4k: rand() calls, 4k+1: gamma == 1 flag
+      const int npts = 2 * k - 1;
+      double *ax = P.ext_phase ? P.ext_aux + (size_t)c_local * (4 * k + 2) : nullptr;
+      double *xprop = P.ext_phase ? P.ext_prop + (size_t)c_local * npts * ld : nullptr;
+      const double *xlike = P.ext_phase >= 2 ? P.ext_like + (size_t)c_local * npts : nullptr;
+      if (P.ext_phase <= 1) {
+        for (int guard = 0;; ++guard) {                                                // Dream.py:278-289
+          gamma_one = gen_eval_batch_mt<G, R>(c, s, dc, k, M, x0, 0, false, pri, lik, snk, D0);
+          if (P.ext_phase == 1) break;
+          bool anyfinite = false;
+          for (int p = 0; p < k; ++p) anyfinite |= isfinite(1.0 * lik[p] + pri[p]);
+          if (anyfinite || guard >= 1000) break;
+        }
+        if (P.ext_phase == 1) {   // hand the k proposals to the caller
+          for (int p = 0; p < k; ++p) {
+            load_slot<G, R>(c, c.slots + (size_t)p * ld, q);
+            store_row<G, R>(c, xprop + (size_t)p * ld, q);
+          }
+          if (c.g == 0) {
+            for (int p = 0; p < k; ++p) { ax[p] = pri[p]; ax[k + p] = snk[p]; }
+            ax[2 * k] = (double)s.n_rand;
+          }
+          return;
+        }
+      } else {                    // the proposals' scalars come back; the stream resumes after their draws
+        if (c.g == 0)
+          for (int p = 0; p < k; ++p) { pri[p] = ax[p]; snk[p] = ax[k + p]; lik[p] = xlike[p]; }
+        __syncwarp(c.gmask);
+        advance_batch_counters(s, dc, k);
+        s.n_rand = (uint32_t)ax[2 * k];
+        if (P.ext_phase == 2) {   // the regenerate loop of Dream.py:282-289 needs new draws: not available in the split step
+          bool anyfinite = false;
+          for (int p = 0; p < k; ++p) anyfinite |= isfinite(1.0 * lik[p] + pri[p]);
+          if (!anyfinite && c.g == 0) atomicExch(P.ext_error, 1);
+        }
       }
-      // mt_choose_proposal_pt, Dream.py:883-917
-      double mx = 1.0 * lik[0] + pri[0];
-      for (int p = 1; p < k; ++p) { const double v = 1.0 * lik[p] + pri[p]; if (v > mx) mx = v; }
-      double prob[DREAMZS_MAX_MULTITRY], sum = 0.0;
-      for (int p = 0; p < k; ++p) { prob[p] = exp((1.0 * lik[p] + pri[p]) - mx); sum = (p == 0) ? prob[0] : sum + prob[p]; }
-      for (int p = 0; p < k; ++p) prob[p] = prob[p] / sum;
-      sel = multinomial_index(s, prob, k);
-      load_slot<G, R>(c, c.slots + (size_t)sel * ld, q);
-      // reference set around the selected proposal, Dream.py:295-303
-      gamma_one = gen_eval_batch_mt<G, R>(c, s, dc, k - 1, M, q, k, true, rpri, rlik, rsnk, D0);
+      if (P.ext_phase <= 2) {
+        // mt_choose_proposal_pt, Dream.py:883-917
+        double mx = 1.0 * lik[0] + pri[0];
+        for (int p = 1; p < k; ++p) { const double v = 1.0 * lik[p] + pri[p]; if (v > mx) mx = v; }
+        double prob[DREAMZS_MAX_MULTITRY], sum = 0.0;
+        for (int p = 0; p < k; ++p) { prob[p] = exp((1.0 * lik[p] + pri[p]) - mx); sum = (p == 0) ? prob[0] : sum + prob[p]; }
+        for (int p = 0; p < k; ++p) prob[p] = prob[p] / sum;
+        sel = multinomial_index(s, prob, k);
+      } else {
+        sel = (int)ax[2 * k + 1];
+        s.n_multinomial += 1;
+      }
+      if (P.ext_phase == 0) load_slot<G, R>(c, c.slots + (size_t)sel * ld, q);
+      else {
+        const double *prow = xprop + (size_t)sel * ld;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i0 = c.dim0(r);
+          if (i0 < ld) {
+            const double2 a = *reinterpret_cast<const double2 *>(prow + i0), b = *reinterpret_cast<const double2 *>(prow + i0 + 2);
+            q[r][0] = a.x; q[r][1] = a.y; q[r][2] = b.x; q[r][3] = b.y;
+          } else q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0.0;
+        }
+      }
+      if (P.ext_phase <= 2) {
+        // reference set around the selected proposal, Dream.py:295-303
+        gamma_one = gen_eval_batch_mt<G, R>(c, s, dc, k - 1, M, q, k, P.ext_phase == 0, rpri, rlik, rsnk, D0);
+        if (P.ext_phase == 2) {   // hand the k-1 reference points to the caller
+          double rq[R][4];
+          for (int p = 0; p < k - 1; ++p) {
+            load_slot<G, R>(c, c.slots + (size_t)(k + p) * ld, rq);
+            store_row<G, R>(c, xprop + (size_t)(k + p) * ld, rq);
+          }
+          if (c.g == 0) {
+            ax[2 * k + 1] = (double)sel;
+            for (int p = 0; p < k - 1; ++p) { ax[2 * k + 2 + p] = rpri[p]; ax[3 * k + 1 + p] = rsnk[p]; }
+            ax[4 * k] = (double)s.n_rand;
+            ax[4 * k + 1] = gamma_one ? 1.0 : 0.0;
+          }
+          return;
+        }
+      } else {
+        if (c.g == 0)
+          for (int p = 0; p < k - 1; ++p) { rpri[p] = ax[2 * k + 2 + p]; rsnk[p] = ax[3 * k + 1 + p]; rlik[p] = xlike[k + p]; }
+        __syncwarp(c.gmask);
+        advance_batch_counters(s, dc, k - 1);
+        s.n_rand = (uint32_t)ax[4 * k];
+        gamma_one = ax[4 * k + 1] != 0.0;
+      }
       double tp[DREAMZS_MAX_MULTITRY], trf[DREAMZS_MAX_MULTITRY];
       double m2 = -INFINITY;
       for (int p = 0; p < k; ++p) {

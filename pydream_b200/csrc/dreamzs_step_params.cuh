@@ -26,10 +26,11 @@ struct StepParams {
   uint64_t publish_k;     // != 0: this launch appends; when all local chains have, publish append #publish_k
   unsigned int *peer_counter;   // chains of this launch that have appended (scratch, returns to 0)
   int32_t *peer_error;
-  int32_t ext_phase;      // split step for caller-evaluated likelihoods: 0 fused, 1 propose only, 2 accept only
+  int32_t ext_phase;      // split step for caller-evaluated likelihoods: 0 fused; single try: 1 propose, 2 accept; multi-try: 1 propose, 2 select, 3 accept
   double *ext_prop;       // [nchains_local x ld] proposals (written by phase 1, read by phase 2)
   double *ext_aux;        // [nchains_local x 4]  log prior, snooker logp, |x - z|^2, gamma == 1 flag
   const double *ext_like; // [nchains_local]      caller's log-likelihood of the proposals (phase 2)
+  int32_t *ext_error;     // set to 1 when a multi-try batch has no finite log-posterior (the regenerate loop is not split)
   long long *dbg;         // optional phase-timestamp buffer (dreamzs_debug_set_phase_buffer; profiling aid)
   int32_t gw_append;      // window kernel: the last iteration of the launch appends to the archive
   int32_t gw_refresh;     // window kernel: re-derive gauss_Y / gauss_Q from X at the start of the launch

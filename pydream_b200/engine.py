@@ -134,8 +134,6 @@ class DreamEngine:
         self.peers = None
         self._shared = None          # (own base pointer, [opened peer base pointers])
         self.external = target.kind == T.TARGET_EXTERNAL     # likelihood evaluated by the caller: split step
-        if self.external and multitry != 1:
-            raise NotImplementedError('multi-try with a caller-evaluated likelihood (TorchLikelihood) is not implemented')
         self._want_peers = bool(peer_archive) and self.world > 1 and self.world <= _cabi.MAX_PEERS and not self.external
         # the archive is sized once for `reserve_iters` iterations (it grows on demand beyond that)
         self._ensure_capacity(self.nseed + appends_in(0, int(reserve_iters), self.thin) * N)
@@ -183,8 +181,12 @@ class DreamEngine:
         _cabi.check(self.lib.dreamzs_init_logp(C.byref(self.cfg), C.byref(self.st), self._stream()), 'dreamzs_init_logp')
         self.launches += 1
         if self.external:
-            self._prop = torch.zeros((self.Nl, self.ld), **f64)
-            self._aux = torch.zeros((self.Nl, 4), **f64)
+            k = int(multitry)
+            self._mt = k
+            self._prop = torch.zeros((self.Nl, 2 * k - 1, self.ld), **f64)     # proposals, then the reference set
+            self._aux = torch.zeros((self.Nl, 4 if k == 1 else 4 * k + 2), **f64)
+            self._like = torch.zeros((self.Nl, 2 * k - 1), **f64)
+            self._ext_error = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.last_like.copy_(target.evaluate(self.X[:, :d].contiguous()))     # first-call logp, Dream.py:266-268
 
     # ------------------------------------------------------------------ plumbing
@@ -308,7 +310,11 @@ class DreamEngine:
             self._release_shared()
 
     def check_peers(self):
-        """Raise if a wait for a peer's append timed out (DREAMZS_PEER_TIMEOUT_NS)."""
+        """Raise if a wait for a peer's append timed out (DREAMZS_PEER_TIMEOUT_NS), or if a multi-try batch of the split
+        step had no finite log-posterior (the reference would redraw it, Dream.py:282-289)."""
+        if self.external and int(self._ext_error.item()) != 0:
+            raise _cabi.DreamzsError('every proposal of a multi-try batch had a non-finite log-posterior: the split step '
+                                     'cannot redraw it')
         if self._shared is not None:
             err = self._shared['block'][1024:1028].view(torch.int32)
             if int(err.item()) != 0:
@@ -383,10 +389,16 @@ class DreamEngine:
         if adapting and t_first <= self.crossover_burnin:
             x_entry = self.X.clone()
         for t in range(t_first, t_first + niter):
+            k, d = self._mt, self.d
             _cabi.check(lib.dreamzs_propose(cfg, st, t, self.archive_rows, p(self._prop), p(self._aux), stream), 'dreamzs_propose')
-            like = self.target.evaluate(self._prop[:, :self.d].contiguous() if self.ld != self.d else self._prop)
+            self._like[:, :k] = self.target.evaluate(self._prop[:, :k, :d].reshape(-1, d).contiguous()).view(self.Nl, k)
+            if k > 1:      # multi-try: pick a proposal, then the reference set around it (Dream.py:291-303)
+                _cabi.check(lib.dreamzs_select(cfg, st, t, self.archive_rows, p(self._prop), p(self._aux), p(self._like),
+                                               p(self._ext_error), stream), 'dreamzs_select')
+                self._like[:, k:] = self.target.evaluate(self._prop[:, k:, :d].reshape(-1, d).contiguous()).view(self.Nl, k - 1)
+                self.launches += 1
             tr.trace_offset = t - t_first
-            _cabi.check(lib.dreamzs_accept(cfg, st, C.byref(tr), t, self.archive_rows, p(self._prop), p(self._aux), p(like), stream),
+            _cabi.check(lib.dreamzs_accept(cfg, st, C.byref(tr), t, self.archive_rows, p(self._prop), p(self._aux), p(self._like), stream),
                         'dreamzs_accept')
             self.launches += 2
             if adapting and ((10 < t < self.crossover_burnin) or t == self.crossover_burnin):

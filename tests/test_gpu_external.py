@@ -71,5 +71,39 @@ def test_external_with_bounded_prior_and_run_dream():
         assert np.all(s[c] >= lower) and np.all(s[c] <= upper)
     # as a host callable (the reference's likelihood(param_vec) -> float contract)
     assert abs(ext(np.array([1., 2, 3, 4])) - 22.0) < 1e-12
-    with pytest.raises(NotImplementedError):
-        run_dream(params, ext, multitry=5, **kw)
+
+
+@pytest.mark.parametrize('k,snooker', [(5, .2), (3, 0.)])
+def test_external_multitry_equals_fused(k, snooker):
+    """multi-try through dreamzs_propose -> fn -> dreamzs_select -> fn -> dreamzs_accept (Dream.py:275-323)."""
+    from pydream_b200.engine import DreamEngine
+    d, N, T = 10, 80, 36
+    rng = np.random.default_rng(13)
+    hist = rng.normal(size=(2 * N + 7, d)) * 3
+    tgt = targets.BimodalMixture.benchmark(d)
+    kw = dict(seed=32, snooker=snooker, history_thin=4, multitry=k)
+    a = _run(DreamEngine(d, N, hist, hist[:N], tgt, **kw), T)
+    eng = DreamEngine(d, N, hist, hist[:N], targets.TorchLikelihood(d, _torch_mixture(tgt)), **kw)
+    b = _run(eng, T)
+    eng.check_peers()
+    np.testing.assert_array_equal(a[2], b[2])
+    assert np.all(np.abs(a[1] - b[1]) <= logp_tol(a[1])), (np.abs(a[1] - b[1]) / logp_tol(a[1])).max()
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=1e-13)
+
+
+def test_external_multitry_bounded_prior():
+    """multi-try + uniform prior: the boundary redraws (np.random.rand, Dream.py:749-775) keep their place in the stream
+    across the three phases."""
+    from pydream_b200.core import run_dream
+    from pydream_b200.parameters import SampledParam
+    lower, upper = np.array([-5., -9, 5, 3]), np.array([10., 2, 7, 8])
+    params = [SampledParam(uniform, loc=lower, scale=upper - lower)]
+    rng = np.random.default_rng(4)
+    hist = rng.uniform(lower, upper, size=(64, 4))
+    kw = dict(niterations=150, nchains=7, start=[hist[c] for c in range(7)], start_random=False, history_file=hist,
+              verbose=False, save_history=False, seed=10, multitry=3)
+    ref_s, ref_l = run_dream(params, targets.SumShift(4, 3.0), **kw)
+    s, l = run_dream(params, targets.TorchLikelihood(4, lambda x: (x + 3.0).sum(dim=1)), **kw)
+    for c in range(7):
+        np.testing.assert_allclose(s[c], ref_s[c], rtol=1e-12)
+        np.testing.assert_allclose(l[c], ref_l[c], rtol=1e-12)

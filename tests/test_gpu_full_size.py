@@ -84,3 +84,15 @@ def test_c5_shape_adaptation_and_rhat():
     W = tr.var(axis=1).mean(axis=0)
     B = tr.mean(axis=1).var(axis=0)
     np.testing.assert_allclose(rhat, np.sqrt((W * (1 - 1. / T) + B) / W), rtol=1e-10)
+
+
+def test_c4_shape_banana_200d():
+    """200-D twisted Gaussian (two chunk rounds per lane), the per-GPU share of config 4 at 2 GPUs."""
+    from pydream_b200.engine import DreamEngine
+    d, N, T, thin, nseed = 200, 4096, 30, 10, 16384
+    rng = np.random.default_rng(45)
+    tgt = targets.Banana(d, 0.1)
+    hist = rng.normal(size=(nseed, d)) * np.sqrt(np.concatenate([[100.0], np.ones(d - 1)]))
+    eng = DreamEngine(d, N, hist, hist[:N], tgt, seed=7, snooker=.1, history_thin=thin)
+    trace, logp, dec = eng.run(T)
+    _check_invariants(eng, trace, logp, dec, tgt, nseed, thin, hist[:N])

@@ -164,6 +164,7 @@ def test_c_abi_argument_checks_without_a_gpu():
     assert lib.dreamzs_copy_d2h_2d(None, 8, None, 8, 8, 1, None) == _cabi.E_BADARG
     assert lib.dreamzs_propose(C.byref(cfg), C.byref(st), 0, 16, None, None, None) == _cabi.E_BADARG
     assert lib.dreamzs_accept(C.byref(cfg), C.byref(st), C.byref(tr), 0, 16, None, None, None, None) == _cabi.E_BADARG
+    assert lib.dreamzs_select(C.byref(cfg), C.byref(st), 0, 16, None, None, None, None, None) == _cabi.E_BADARG
     assert lib.dreamzs_shared_alloc(0, None, None) == _cabi.E_BADARG
     assert lib.dreamzs_gr_finish(None, None, 1, 1, 1, None, None) == _cabi.E_BADARG
 
