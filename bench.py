@@ -8,9 +8,18 @@ Workload (BASELINE.json configs[1], SURVEY.md 8(d) "C2"): 100-D correlated Gauss
 (dream_ex_ndim_gaussian.py covariance), 1024 chains per GPU, FlatParam prior, reference default options
 (snooker .1, DEpairs 1, nCR 3, history_thin 10, multitry off), crossover adaptation off so that the timed
 region is the steady-state step.  One "step" = one sampler iteration of every chain (1024 chain-steps per
-GPU).  The archive is pre-seeded with 262144 rows (210 MB > the 126 MB L2) so every timed gather works on
-an input larger than L2.  Scaling over GPUs is weak: 1024 chains per GPU, archive replicated, new rows
-all-gathered over NCCL every history_thin iterations.
+GPU); a launch of the dense-Gaussian window kernel fuses the 10 iterations of one history_thin window.
+The archive is pre-seeded with 262144 rows (210 MB > the 126 MB L2) so every timed gather works on an input
+larger than L2.  Scaling over GPUs is weak: 1024 chains per GPU, archive replicated, the rows appended every
+history_thin iterations reach the other replicas as NVLink peer stores from inside the step kernel (NCCL
+all-gather when peer mappings are unavailable).
+
+`value`  : K steps through DreamEngine.run with everything resident in HBM, CUDA events, max over ranks.
+`e2e`    : the same metric through pydream_b200.core.run_dream with host (numpy) inputs and outputs: archive
+           seed + starts uploaded, every sample and log-posterior copied back, inside the timed region.
+`roofline`: algorithmic HBM bytes per chain-step x chain-steps per launch / launch duration,
+           against the measured copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` (N=1): oracle/dreamzs_oracle.c (a C port of the reference's step) on the host threads, bounded sample.
 """
 import argparse
 import json
