@@ -178,3 +178,23 @@ def test_window_kernel_dimensions(d):
     np.testing.assert_array_equal(dec, ref['decisions'])
     assert np.all(np.abs(logp - ref['logp']) <= logp_tol(ref['logp']))
     np.testing.assert_allclose(states, ref['states'], rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize('kw', [
+    dict(nCR=5, gamma_levels=3, adapt_gamma=True, adapt_crossover=True, crossover_burnin=30, snooker=.15, history_thin=6),
+    dict(nCR=16, gamma_levels=8, snooker=.1, history_thin=1, p_gamma_unity=.5),
+    dict(nCR=1, snooker=0., history_thin=25, p_gamma_unity=0., lamb=.2, zeta=1e-6),
+], ids=['adapt_cr_and_gamma', 'max_tables_thin1', 'no_snooker_long_window'])
+def test_window_kernel_option_space(kw):
+    """Corners of the option space on the window kernel against the generic kernel (same draws): many CR values and
+    gamma levels with both adaptations during burn-in, a window of one iteration, a window longer than a batch."""
+    from pydream_b200.engine import DreamEngine
+    rng = np.random.default_rng(91)
+    d, N, T = 80, 77, 52
+    tgt = make_target(dict(kind='gaussian', d=d))
+    hist = rng.uniform(-5, 15, size=(2 * N + 5, d))
+    a = _run(DreamEngine(d, N, hist, hist[:N], tgt, seed=12, **kw), T)
+    b = _run(DreamEngine(d, N, hist, hist[:N], tgt, seed=12, generic_kernel=True, **kw), T)
+    np.testing.assert_array_equal(a[2], b[2])
+    assert np.all(np.abs(a[1] - b[1]) <= logp_tol(b[1])), (np.abs(a[1] - b[1]) / logp_tol(b[1])).max()
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-10, atol=1e-11)
