@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 MAX_NCR, MAX_NGAMMA = 16, 8
+ABI_VERSION = 2     # DREAMZS_ABI_VERSION of include/dreamzs.h (checked by dreamzs_oracle_run)
 
 
 class Config(C.Structure):
@@ -23,7 +24,8 @@ class State(C.Structure):
     _fields_ = [('Z', C.c_void_p), ('Z_capacity_rows', C.c_int64), ('X', C.c_void_p), ('last_prior', C.c_void_p),
                 ('last_like', C.c_void_p), ('cr_probs', C.c_void_p), ('gamma_probs', C.c_void_p),
                 ('gamma_table', C.c_void_p), ('target_table', C.c_void_p), ('prior_kind', C.c_void_p),
-                ('prior_a', C.c_void_p), ('prior_b', C.c_void_p), ('mins', C.c_void_p), ('maxs', C.c_void_p)]
+                ('prior_a', C.c_void_p), ('prior_b', C.c_void_p), ('mins', C.c_void_p), ('maxs', C.c_void_p),
+                ('gauss_Y', C.c_void_p), ('gauss_Q', C.c_void_p)]     # unused by the oracle (NULL)
 
 
 class Adapt(C.Structure):
@@ -34,8 +36,8 @@ class Adapt(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, 'libdreamzs_oracle.so')
-    src = os.path.join(_HERE, 'dreamzs_oracle.c')
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, 'dreamzs_oracle.c'), os.path.join(_HERE, '..', 'include', 'dreamzs.h')]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(['make', '-s', '-C', _HERE, '-B', 'libdreamzs_oracle.so'])
     return so
 
@@ -92,7 +94,7 @@ class OracleSampler:
         self.last_prior, self.last_like = np.zeros(N), np.zeros(N)
         self.count = C.c_int64(0)
         self.nthreads = int(nthreads)
-        self.cfg = Config(abi_version=1, ndim=d, ld=self.ld, nchains_global=N, chain_begin=0, nchains_local=N,
+        self.cfg = Config(abi_version=ABI_VERSION, ndim=d, ld=self.ld, nchains_global=N, chain_begin=0, nchains_local=N,
                           nCR=nCR, ngamma=gamma_levels, nDEpairs=DEpairs, multitry=multitry,
                           hardboundaries=int(bool(hardboundaries)), history_thin=history_thin,
                           target_kind=int(target_kind), snooker=snooker, p_gamma_unity=p_gamma_unity, lamb=lamb,

@@ -370,7 +370,7 @@ static uint32_t chain_step(const dreamzs_config *cfg, const dreamzs_state *st, i
       DBG_ROWS(b);
     }
     /* mt_choose_proposal_pt, Dream.py:883-917 */
-    double mx = lps[0], w[DREAMZS_MAX_MULTITRY], prob[DREAMZS_MAX_MULTITRY], sum = 0.0;
+    double mx = lps[0], w[DREAMZS_MAX_MULTITRY] = {0}, prob[DREAMZS_MAX_MULTITRY], sum = 0.0;
     for (int p = 1; p < k; ++p) if (lps[p] > mx) mx = lps[p];
     for (int p = 0; p < k; ++p) w[p] = exp(lps[p] - mx);
     sum = np_sum(w, k);
