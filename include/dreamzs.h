@@ -125,10 +125,13 @@ typedef struct dreamzs_trace {
   uint32_t *decisions;  /* nchains_local x trace_iters : bit0 accept (state changed), bit1 snooker,
                            bits2-5 CR index, bits6-9 gamma-level index, bits10-13 DE pairs,
                            bits14-17 selected multi-try index, bit18 gamma==1 flag used by CR adaptation,
-                           bit19 metropolis accepted */
+                           bit19 metropolis accepted, bit20 (tempered runs, swap rows only) state exchanged
+                           with another chain */
   int64_t trace_iters;  /* iterations the trace buffers hold per chain */
   int64_t trace_offset; /* trace row that iteration `iter_begin` writes to */
 } dreamzs_trace;
+
+#define DREAMZS_DECISION_SWAPPED (1u << 20)
 
 int dreamzs_abi_version(void);
 

@@ -47,6 +47,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.dreamzs_oracle_run.restype = C.c_int
+        _LIB.dreamzs_oracle_run_pt.restype = C.c_int
         _LIB.dreamzs_oracle_work_doubles.restype = C.c_int64
     return _LIB
 
@@ -72,6 +73,11 @@ def gelman_rubin(trace):
     out = np.zeros(d)
     lib().dreamzs_oracle_gelman_rubin(_p(trace), C.c_int64(n), C.c_int64(s), C.c_int32(d), C.c_int64(d), _p(out))
     return out
+
+
+def temperature_ladder(nchains):
+    """T[i] = 0.001 ** (i / nchains), pydream/core.py:133-136."""
+    return np.array([np.power(.001, (float(i) / nchains)) for i in range(nchains)])
 
 
 class OracleSampler:
@@ -156,6 +162,24 @@ class OracleSampler:
         if rows is not None:
             out['rows'] = rows.transpose(1, 0, 2).copy()
         return out
+
+    def run_pt(self, niter, temperature=None):
+        """Parallel tempering (pydream/core.py:131-236).  Returns dict(sampled_params (N, 2 niter, d), log_ps (N, 2 niter),
+        decisions (N, 2 niter), swaps (niter, 3) = first chain, second chain, accepted)."""
+        niter = int(niter)
+        self.ensure_capacity(niter)
+        T = temperature_ladder(self.N) if temperature is None else np.ascontiguousarray(temperature, dtype=np.float64)
+        trace = np.zeros((self.N, 2 * niter, self.ld))
+        logp = np.zeros((self.N, 2 * niter))
+        dec = np.zeros((self.N, 2 * niter), dtype=np.uint32)
+        swaps = np.zeros((niter, 3), dtype=np.int64)
+        rc = lib().dreamzs_oracle_run_pt(C.byref(self.cfg), C.byref(self.st), C.byref(self.ad), _p(T), C.c_int64(self.iter),
+                                         C.c_int64(niter), C.c_int64(self.nseed), C.byref(self.count), _p(trace), _p(logp),
+                                         _p(dec), _p(swaps), C.c_int32(self.nthreads))
+        if rc != 0:
+            raise RuntimeError('dreamzs_oracle_run_pt failed: %d' % rc)
+        self.iter += niter
+        return dict(sampled_params=np.ascontiguousarray(trace[:, :, :self.d]), log_ps=logp, decisions=dec, swaps=swaps)
 
     @property
     def history_flat(self):

@@ -310,7 +310,7 @@ typedef struct { double *buf; } scratch_t;
  * the caller after the sweep.  Returns the decision word (include/dreamzs.h). */
 static uint32_t chain_step(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int c_local,
                            int64_t M, const double *cr_probs, const double *gamma_probs, double *q_new,
-                           double *work, int64_t *rows_dbg, int rows_dbg_n) {
+                           double *work, int64_t *rows_dbg, int rows_dbg_n, double T) {
   const int d = cfg->ndim, ld = cfg->ld, k = cfg->multitry;
   const int c_global = cfg->chain_begin + c_local;
   const double *q0 = st->X + (size_t)c_local * ld;
@@ -332,7 +332,7 @@ static uint32_t chain_step(const dreamzs_config *cfg, const dreamzs_state *st, i
   double snk[DREAMZS_MAX_MULTITRY], rsnk[DREAMZS_MAX_MULTITRY];
   batch_t b; b.pts = pts; b.snk_logp = snk; b.zrow = zrow;
   double last_prior = st->last_prior[c_local], last_like = st->last_like[c_local];
-  double last_logp = 1.0 * last_like + last_prior;
+  double last_logp = T * last_like + last_prior;   /* Dream.py:243, 268 */
   int accepted = 0, sel = 0, gamma_one;
   double new_prior = 0, new_like = 0;
   const double *q_prop;
@@ -345,7 +345,7 @@ static uint32_t chain_step(const dreamzs_config *cfg, const dreamzs_state *st, i
   gamma_one = b.gamma_any_one == 1.0;
   if (k == 1) {
     double q_prior = log_prior(cfg, st, pts, tmp), q_like = log_like(cfg, st, pts, tmp);
-    double q_logp = 1.0 * q_like + q_prior, mr;
+    double q_logp = T * q_like + q_prior, mr;   /* Dream.py:274 */
     if (dc.run_snooker) {   /* Dream.py:326-332 */
       for (int i = 0; i < d; ++i) tmp[i] = q0[i] - zrow[i];
       double norm = sqrt(dot(tmp, tmp, d));
@@ -362,7 +362,7 @@ static uint32_t chain_step(const dreamzs_config *cfg, const dreamzs_state *st, i
       for (int p = 0; p < k; ++p) {
         pri[p] = log_prior(cfg, st, pts + (size_t)p * d, tmp);
         lik[p] = log_like(cfg, st, pts + (size_t)p * d, tmp);
-        lps[p] = 1.0 * lik[p] + pri[p];
+        lps[p] = T * lik[p] + pri[p];   /* Dream.py:279, 899 */
         anyfinite |= isfinite(lps[p]) != 0;
       }
       if (anyfinite || guard >= 1000) break;
@@ -387,7 +387,7 @@ static uint32_t chain_step(const dreamzs_config *cfg, const dreamzs_state *st, i
       rlik[p] = log_like(cfg, st, rpts + (size_t)p * d, tmp);
     }
     rlik[k - 1] = last_like; rpri[k - 1] = last_prior;   /* Dream.py:877-879 */
-    for (int p = 0; p < k; ++p) rlps[p] = 1.0 * rlik[p] + rpri[p];
+    for (int p = 0; p < k; ++p) rlps[p] = T * rlik[p] + rpri[p];   /* Dream.py:303 */
     double tp[DREAMZS_MAX_MULTITRY], trf[DREAMZS_MAX_MULTITRY];
     if (dc.run_snooker) {   /* Dream.py:306-313 */
       rsnk[k - 1] = 0.0;
@@ -489,6 +489,8 @@ typedef struct {
   int nthreads; int64_t niter, iter, it, M; int stop;
   double *work, *Xnew; uint32_t *dec; int64_t wd; int64_t *rows_dbg; int rows_dbg_n;
   double crp[DREAMZS_MAX_NCR], gp[DREAMZS_MAX_NGAMMA];
+  const double *temperature;   /* per chain; NULL = 1 (no tempering) */
+  int64_t rows_per_iter;       /* trace rows per iteration: 1, or 2 under parallel tempering */
   pthread_barrier_t go, done;
 } pool_t;
 typedef struct { pool_t *pl; int tid; } worker_arg_t;
@@ -502,7 +504,7 @@ static void sweep_slice(pool_t *pl, int tid) {
     pl->dec[c] = chain_step(cfg, pl->st, pl->iter, c, pl->M, pl->crp, pl->gp, pl->Xnew + (size_t)c * ld,
                             pl->work + (size_t)tid * pl->wd,
                             pl->rows_dbg ? pl->rows_dbg + ((size_t)c * pl->niter + pl->it) * pl->rows_dbg_n : NULL,
-                            pl->rows_dbg_n);
+                            pl->rows_dbg_n, pl->temperature ? pl->temperature[c] : 1.0);
   }
 }
 static void *worker_main(void *p) {
@@ -519,11 +521,12 @@ static void *worker_main(void *p) {
  * st->Z/X/last_* are HOST pointers here.  trace: N x niter x ld, trace_logp: N x niter,
  * decisions: N x niter (may be NULL), rows_dbg: N x niter x rows_dbg_n (may be NULL).
  * *count is Dream_shared_vars.count (rows appended so far), nseed = nseedchains. */
-int dreamzs_oracle_run(const dreamzs_config *cfg, const dreamzs_state *st, dreamzs_oracle_adapt *ad,
-                       int64_t iter_begin, int64_t niter, int64_t nseed, int64_t *count, double *trace,
-                       double *trace_logp, uint32_t *decisions, int64_t *rows_dbg, int32_t rows_dbg_n,
-                       int32_t nthreads) {
+static int run_impl(const dreamzs_config *cfg, const dreamzs_state *st, dreamzs_oracle_adapt *ad,
+                    int64_t iter_begin, int64_t niter, int64_t nseed, int64_t *count, double *trace,
+                    double *trace_logp, uint32_t *decisions, int64_t *rows_dbg, int32_t rows_dbg_n,
+                    int32_t nthreads, const double *temperature, int64_t *swap_pairs) {
   const int N = cfg->nchains_local, ld = cfg->ld;
+  const int64_t rpi = temperature ? 2 : 1, TR = niter * rpi;   /* trace rows per iteration / per chain */
   if (cfg->abi_version != DREAMZS_ABI_VERSION || cfg->multitry < 1 || cfg->multitry > DREAMZS_MAX_MULTITRY ||
       cfg->multitry == 2 || cfg->nDEpairs > DREAMZS_MAX_DEPAIRS || cfg->nCR > DREAMZS_MAX_NCR)
     return DREAMZS_E_BADARG;
@@ -531,6 +534,7 @@ int dreamzs_oracle_run(const dreamzs_config *cfg, const dreamzs_state *st, dream
   if (nthreads > N) nthreads = N;
   pool_t pl; memset(&pl, 0, sizeof(pl));
   pl.cfg = cfg; pl.st = st; pl.nthreads = nthreads; pl.niter = niter; pl.rows_dbg = rows_dbg; pl.rows_dbg_n = rows_dbg_n;
+  pl.temperature = temperature; pl.rows_per_iter = rpi;
   pl.wd = dreamzs_oracle_work_doubles(cfg);
   pl.work = (double *)malloc(sizeof(double) * (size_t)pl.wd * nthreads);
   pl.Xnew = (double *)malloc(sizeof(double) * (size_t)N * ld);
@@ -556,14 +560,41 @@ int dreamzs_oracle_run(const dreamzs_config *cfg, const dreamzs_state *st, dream
     if (nthreads > 1) pthread_barrier_wait(&pl.done);
     adapt_sweep(cfg, ad, iter, st->X, pl.Xnew, pl.dec);
     for (int c = 0; c < N; ++c) {
+      const double Tc = temperature ? temperature[c] : 1.0;
       memcpy(st->X + (size_t)c * ld, pl.Xnew + (size_t)c * ld, sizeof(double) * ld);
-      memcpy(trace + ((size_t)c * niter + it) * ld, pl.Xnew + (size_t)c * ld, sizeof(double) * ld);
-      trace_logp[(size_t)c * niter + it] = st->last_like[c] + st->last_prior[c];   /* core.py:115 */
-      if (decisions) decisions[(size_t)c * niter + it] = pl.dec[c];
+      memcpy(trace + ((size_t)c * TR + it * rpi) * ld, pl.Xnew + (size_t)c * ld, sizeof(double) * ld);
+      trace_logp[(size_t)c * TR + it * rpi] = Tc * st->last_like[c] + st->last_prior[c];   /* core.py:115; :178 under tempering */
+      if (decisions) decisions[(size_t)c * TR + it * rpi] = pl.dec[c];
     }
     if (appends) {   /* record_history, Dream.py:360-362, 919-938 */
       for (int c = 0; c < N; ++c) memcpy(st->Z + (size_t)(M + c) * ld, pl.Xnew + (size_t)c * ld, sizeof(double) * ld);
       *count += N;
+    }
+    if (temperature) {
+      /* temperature swap of _sample_dream_pt (pydream/core.py:183-218): the parent process draws a pair of
+       * chains and a uniform from the stream of the pseudo-chain 0xFFFFFFFF (oracle/philox.py), exchanges
+       * state, log-likelihood and log-prior when log(u) < alpha, and records every chain a second time. */
+      stream_t ds; stream_init(&ds, cfg->seed, 0xFFFFFFFFu, (uint32_t)iter);
+      int64_t pr[2]; stream_sample(&ds, cfg->nchains_global, 2, pr);
+      const int a = (int)pr[0], b = (int)pr[1];
+      const double T1 = temperature[a], T2 = temperature[b], l1 = st->last_like[a], l2 = st->last_like[b];
+      const double alpha = ((T1 * l2) + (T2 * l1)) - ((T1 * l1) + (T2 * l2));
+      const int swap = log(stream_uniform53(&ds, ST_UNIFORM_SCAL)) < alpha;
+      if (swap_pairs) { swap_pairs[3 * it] = a; swap_pairs[3 * it + 1] = b; swap_pairs[3 * it + 2] = swap; }
+      for (int c = 0; c < N; ++c)   /* logpnews, with the temperature of the chain that produced it (core.py:176, 207-208) */
+        trace_logp[(size_t)c * TR + it * rpi + 1] = trace_logp[(size_t)c * TR + it * rpi];
+      if (swap) {
+        for (int i = 0; i < ld; ++i) { double t = st->X[(size_t)a * ld + i]; st->X[(size_t)a * ld + i] = st->X[(size_t)b * ld + i]; st->X[(size_t)b * ld + i] = t; }
+        double t = st->last_like[a]; st->last_like[a] = st->last_like[b]; st->last_like[b] = t;
+        t = st->last_prior[a]; st->last_prior[a] = st->last_prior[b]; st->last_prior[b] = t;
+        t = trace_logp[(size_t)a * TR + it * rpi + 1];
+        trace_logp[(size_t)a * TR + it * rpi + 1] = trace_logp[(size_t)b * TR + it * rpi + 1];
+        trace_logp[(size_t)b * TR + it * rpi + 1] = t;
+      }
+      for (int c = 0; c < N; ++c) {
+        memcpy(trace + ((size_t)c * TR + it * rpi + 1) * ld, st->X + (size_t)c * ld, sizeof(double) * ld);
+        if (decisions) decisions[(size_t)c * TR + it * rpi + 1] = (swap && (c == a || c == b)) ? DREAMZS_DECISION_SWAPPED : 0u;
+      }
     }
   }
   if (nthreads > 1) {
@@ -575,6 +606,27 @@ int dreamzs_oracle_run(const dreamzs_config *cfg, const dreamzs_state *st, dream
   }
   free(pl.work); free(pl.Xnew); free(pl.dec);
   return rc;
+}
+
+int dreamzs_oracle_run(const dreamzs_config *cfg, const dreamzs_state *st, dreamzs_oracle_adapt *ad,
+                       int64_t iter_begin, int64_t niter, int64_t nseed, int64_t *count, double *trace,
+                       double *trace_logp, uint32_t *decisions, int64_t *rows_dbg, int32_t rows_dbg_n,
+                       int32_t nthreads) {
+  return run_impl(cfg, st, ad, iter_begin, niter, nseed, count, trace, trace_logp, decisions, rows_dbg, rows_dbg_n,
+                  nthreads, NULL, NULL);
+}
+
+/* The loop of _sample_dream_pt (pydream/core.py:131-236): every iteration is one astep per chain at the
+ * chain's temperature (recorded), then one proposed temperature swap (recorded again): trace is
+ * N x 2 niter x ld, trace_logp / decisions N x 2 niter, log_ps = T like + prior (core.py:176).
+ * swap_pairs (optional): niter x 3 = (first chain, second chain, accepted). */
+int dreamzs_oracle_run_pt(const dreamzs_config *cfg, const dreamzs_state *st, dreamzs_oracle_adapt *ad,
+                          const double *temperature, int64_t iter_begin, int64_t niter, int64_t nseed,
+                          int64_t *count, double *trace, double *trace_logp, uint32_t *decisions,
+                          int64_t *swap_pairs, int32_t nthreads) {
+  if (!temperature || cfg->nchains_local != cfg->nchains_global) return DREAMZS_E_BADARG;
+  return run_impl(cfg, st, ad, iter_begin, niter, nseed, count, trace, trace_logp, decisions, NULL, 0, nthreads,
+                  temperature, swap_pairs);
 }
 
 /* Gelman_Rubin, pydream/convergence.py:3-20.  trace: nchains x nsamples x ld. */

@@ -19,6 +19,11 @@ successive 4x32-bit outputs of one call.  The mapping primitive -> stream is
     4 UNIFORM_SCAL  np.random.uniform([lo, hi])         Dream.py:618,993
     5 RAND          np.random.rand(m)                   Dream.py:749-751,773-775
     6 RANDINT       np.random.randint(1, n+1, size=1)   Dream.py:580
+
+The parent process of the parallel-tempering driver (pydream/core.py:131-236) draws once per
+iteration from the stream of the pseudo-chain ``DRIVER_CHAIN`` = 0xFFFFFFFF:
+``np.random.choice(nchains, 2, replace=False)`` (core.py:183) = ``Stream.sample(nchains, 2)``
+(stream 1, first pick then second pick) and ``np.random.uniform()`` (core.py:195) = stream 4.
 """
 import numpy as np
 
@@ -29,6 +34,7 @@ W1 = 0xBB67AE85
 MASK = 0xFFFFFFFF
 
 ST_MULTINOMIAL, ST_SAMPLE, ST_NORMAL, ST_UNIFORM_VEC, ST_UNIFORM_SCAL, ST_RAND, ST_RANDINT = range(7)
+DRIVER_CHAIN = 0xFFFFFFFF
 
 TWO_M32 = 2.0 ** -32
 TWO_M53 = 2.0 ** -53

@@ -21,6 +21,11 @@ Mechanics (nothing in /root/reference is edited):
     iteration t read the archive as it stood after iteration t-1).
   * the burn-in barrier (Dream.py:385-407) is satisfied by presetting the shared counter so
     each chain sees "all finished" on arrival.
+  * parallel tempering (`run_lockstep_pt`): the reference's own driver ``_sample_dream_pt``
+    (pydream/core.py:131-236) runs unmodified on a stand-in pool whose ``map`` steps the chains in
+    order in this process; the driver's own draws (``np.random.choice(nchains, 2, replace=False)``
+    and ``np.random.uniform()``, core.py:183, 195) are served from the stream of the pseudo-chain
+    ``philox.DRIVER_CHAIN``.
 """
 import copy
 import os
@@ -37,6 +42,7 @@ REF_ROOT = '/root/reference'
 
 class _Ctx:
     stream = None          # philox.Stream of the chain-step being executed
+    driver = None          # philox.Stream of the tempering driver's draws of the current iteration
     log = None             # dict collecting decisions of that chain-step
 
 
@@ -227,4 +233,131 @@ def run_lockstep(make_parameters, likelihood, nchains, niterations, starts, hist
         return out
     finally:
         D.np, D.random, D.time = saved
+        os.chdir(cwd)
+
+
+class _DriverRandomShim:
+    """Stands in for ``np.random`` inside pydream.core (the parent process of the tempering driver)."""
+    log = None
+
+    @staticmethod
+    def choice(n, size, replace=True):
+        assert size == 2 and replace is False
+        pair = _Ctx.driver.sample(int(n), 2)           # first pick, second pick (np.random.choice returns them in draw order)
+        _DriverRandomShim.log['pairs'].append(pair)
+        return np.array(pair)
+
+    @staticmethod
+    def uniform():
+        return _Ctx.driver.uniform53(px.ST_UNIFORM_SCAL)
+
+
+def run_lockstep_pt(make_parameters, likelihood, nchains, niterations, starts, history, seed, **dream_kwargs):
+    """Parallel tempering: the unmodified ``pydream.core._sample_dream_pt`` on a lock-step stand-in pool.
+
+    Returns dict: sampled_params (N, 2*niter, d), log_ps (N, 2*niter, 1) exactly as the reference driver
+    returns them, pairs (niter, 2) the chains proposed for a swap, T (N,) the temperature ladder,
+    log_prior / log_like (niter, N) as returned by astep (before the swap), history_final, cr_probs.
+    """
+    D, C, SV, Model, P = _import_reference()
+    proxy = types.ModuleType('numpy_proxy')
+    proxy.__dict__.update(np.__dict__)
+    proxy.random = _NpRandomShim
+    proxy.log = _masked(np.log)
+    proxy.divide = _masked(np.divide)
+    cproxy = types.ModuleType('numpy_proxy_core')
+    cproxy.__dict__.update(np.__dict__)
+    cproxy.random = _DriverRandomShim
+    saved = (D.np, D.random, D.time, C.np)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix='dreamzs_oracle_')
+    try:
+        os.chdir(tmp)
+        D.np, D.random, D.time, C.np = proxy, _PyRandomShim, _NoSleep, cproxy
+        params = make_parameters(P)
+        model = Model(likelihood=likelihood, sampled_parameters=params)
+        hist_path = os.path.join(tmp, 'seed_history.npy')
+        np.save(hist_path, np.asarray(history, dtype=np.float64))
+        kw = dict(start_random=False, save_history=False, verbose=False, history_file=hist_path)
+        kw.update(dream_kwargs)
+        proto = D.Dream(model=model, variables=params, **kw)
+        start_list = [np.array(s, dtype=np.float64) for s in starts]
+        real_pool = C._setup_mp_dream_pool(nchains, niterations, proto, start_pt=start_list)
+        real_pool._initializer(*real_pool._initargs)
+        real_pool.close()
+        real_pool.join()
+        burnin = proto.crossover_burnin
+        N = nchains
+        extra = dict(log_prior=np.zeros((niterations, N)), log_like=np.zeros((niterations, N)),
+                     cr_probs=np.zeros((niterations, proto.nCR)))
+        _DriverRandomShim.log = dict(pairs=[])
+
+        class LockstepPool:
+            """pool.map(_sample_dream_pt_chain, args) of core.py:173: one astep per chain, in chain order; every worker
+            of the reference holds its own (pickled) Dream instance, here one shallow copy per chain."""
+            def __init__(self):
+                self.chains = None
+                self.queue = []
+                self.t = 0
+
+            def _defer(self, obj, name):
+                real = getattr(obj, name)
+                queue = self.queue
+
+                def wrapper(*a, **kw):
+                    cp = lambda x: np.array(x, dtype=np.float64, copy=True) if isinstance(x, np.ndarray) else x
+                    queue.append((real, tuple(cp(x) for x in a), {k: cp(v) for k, v in kw.items()}))
+                    if name == 'estimate_crossover_probabilities':
+                        return obj.CR_probabilities
+                    if name == 'estimate_gamma_level_probs':
+                        return obj.gamma_probabilities
+                    return None
+                setattr(obj, name, wrapper)
+
+            def map(self, fn, args):
+                t = self.t
+                if self.chains is None:
+                    self.chains = [copy.copy(a[0]) for a in args]
+                    for ch in self.chains:
+                        for name in ('record_history', 'estimate_crossover_probabilities', 'estimate_gamma_level_probs'):
+                            self._defer(ch, name)
+                out = []
+                for c, a in enumerate(args):
+                    _Ctx.stream = px.Stream(seed, c, t)
+                    _Ctx.log = dict(multinomial=[], rows=[])
+                    if t == burnin:
+                        SV.nchains.value = N - 1
+                    res = fn((self.chains[c],) + tuple(a[1:]))
+                    extra['log_prior'][t, c], extra['log_like'][t, c] = res[1], res[2]
+                    out.append(res)
+                for real, a, kw in self.queue:
+                    res = real(*a, **kw)
+                    if real.__name__ == 'estimate_crossover_probabilities':
+                        real.__self__.CR_probabilities = res
+                    elif real.__name__ == 'estimate_gamma_level_probs':
+                        real.__self__.gamma_probabilities = res
+                self.queue.clear()
+                if proto.adapt_crossover and t <= burnin:
+                    shared = list(SV.cross_probs[0:proto.nCR])
+                    for ch in self.chains:
+                        ch.CR_probabilities = shared
+                if proto.adapt_gamma and t <= burnin:
+                    shared = list(SV.gamma_level_probs[0:proto.ngamma])
+                    for ch in self.chains:
+                        ch.gamma_probabilities = shared
+                extra['cr_probs'][t] = np.array(self.chains[0].CR_probabilities, dtype=np.float64)
+                _Ctx.driver = px.Stream(seed, px.DRIVER_CHAIN, t)     # the swap draws that follow this map call
+                self.t = t + 1
+                return out
+
+        sampled, log_ps = C._sample_dream_pt(nchains, niterations, proto, start_list, LockstepPool(), verbose=False)
+        T = np.array([np.power(.001, (float(i) / nchains)) for i in range(nchains)])      # core.py:133-136
+        out = dict(sampled_params=np.array(sampled), log_ps=np.array(log_ps),
+                   pairs=np.array(_DriverRandomShim.log['pairs'], dtype=np.int64), T=T,
+                   history_final=np.frombuffer(SV.history.get_obj()).copy(), count_final=np.array(SV.count.value),
+                   crossover_burnin=np.array(burnin))
+        out.update(extra)
+        return out
+    finally:
+        D.np, D.random, D.time, C.np = saved
         os.chdir(cwd)

@@ -94,6 +94,20 @@ CASES = {
 }
 
 
+# parallel tempering (pydream/core.py:131-236): the reference's own driver on the lock-step pool
+PT_CASES = {
+    'pt_gauss8_snooker': dict(target=dict(kind='gaussian', d=8), prior=dict(kind='flat', d=8), N=6, T=42, nseed=30,
+                              seed=31, hist='lhs', kw=dict(snooker=.2, history_thin=3, adapt_crossover=False)),
+    'pt_norm4_adaptcr_mt3': dict(target=dict(kind='sumshift', d=4),
+                                 prior=dict(kind='norm', loc=[-6.6, 3, 1.0, -.12], scale=[.13, 5, .9, 1.0]), N=5, T=60,
+                                 nseed=20, seed=32, hist='prior_norm',
+                                 kw=dict(adapt_crossover=True, crossover_burnin=30, history_thin=2, nCR=3, multitry=3,
+                                         snooker=.1)),
+    'pt_mix10_de2': dict(target=dict(kind='mixture', d=10), prior=dict(kind='flat', d=10), N=8, T=40, nseed=40,
+                         seed=33, hist='normal', kw=dict(DEpairs=2, snooker=0, history_thin=4, adapt_crossover=False)),
+}
+
+
 def make_history(kind, nseed, d, prior, rng):
     if kind == 'lhs':
         return rng.uniform(-5, 15, size=(nseed, d))
@@ -128,6 +142,20 @@ def main(only=None):
         meta = dict(target=c['target'], prior=c['prior'], N=c['N'], T=c['T'], seed=c['seed'], kw=c['kw'])
         np.savez_compressed(os.path.join(HERE, name + '.npz'), meta=json.dumps(meta), history=hist, starts=starts, **out)
         print(name, 'accept rate %.3f' % out['accept'].mean(), 'rows', int(out['count_final']), flush=True)
+    for name, c in PT_CASES.items():
+        if only and name not in only:
+            continue
+        d = c['target']['d']
+        rng = np.random.default_rng(c['seed'])
+        hist = make_history(c['hist'], c['nseed'], d, c['prior'], rng)
+        starts = hist[:c['N']].copy()
+        tgt = make_target(c['target'])
+        out = H.run_lockstep_pt(make_params(c['prior']), tgt, c['N'], c['T'], starts, hist, seed=c['seed'], **c['kw'])
+        meta = dict(target=c['target'], prior=c['prior'], N=c['N'], T=c['T'], seed=c['seed'], kw=c['kw'], tempering=True)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), meta=json.dumps(meta), history=hist, starts=starts, **out)
+        sp = out['sampled_params']
+        print(name, 'swaps accepted %d of %d' % (int(np.any(sp[:, 0::2] != sp[:, 1::2], axis=(0, 2)).sum()), c['T']),
+              'rows', int(out['count_final']), flush=True)
 
 
 if __name__ == '__main__':

@@ -10,8 +10,17 @@ from pydream_b200 import targets as T
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-def golden_cases():
+def _all_cases():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+
+
+def golden_cases():
+    return [c for c in _all_cases() if not c.startswith('pt_')]
+
+
+def golden_pt_cases():
+    """Parallel-tempering cases (the reference's _sample_dream_pt driver, pydream/core.py:131-236)."""
+    return [c for c in _all_cases() if c.startswith('pt_')]
 
 
 def load_case(name):

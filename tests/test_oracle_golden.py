@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import c_oracle
-from golden_util import golden_cases, load_case, make_target, prior_arrays, sampler_kwargs, decode_decisions, logp_tol
+from golden_util import golden_cases, golden_pt_cases, load_case, make_target, prior_arrays, sampler_kwargs, decode_decisions, logp_tol
 
 
 def run_oracle(meta, z, nthreads=1):
@@ -57,6 +57,38 @@ def test_oracle_matches_reference(name):
     np.testing.assert_allclose(s.gamma_probs, z['gamma_probs'][-1], rtol=1e-12)
     np.testing.assert_allclose(s.delta_m, z['delta_m'], rtol=1e-12)
     np.testing.assert_array_equal(s.ncr_updates, z['ncr_updates'])
+
+
+@pytest.mark.parametrize('name', golden_pt_cases())
+def test_oracle_matches_reference_tempering(name):
+    """Parallel tempering: the C restatement against the reference's own _sample_dream_pt driver
+    (pydream/core.py:131-236) run on the lock-step pool."""
+    meta, z = load_case(name)
+    d = meta['target']['d']
+    tgt = make_target(meta['target'])
+    pk, pa, pb = prior_arrays(meta['prior'], d)
+    s = c_oracle.OracleSampler(d, meta['N'], z['history'], z['starts'], tgt.kind, tgt.table(), seed=meta['seed'],
+                               prior_kind=pk, prior_a=pa, prior_b=pb, **sampler_kwargs(meta))
+    np.testing.assert_array_equal(c_oracle.temperature_ladder(meta['N']), z['T'])
+    out = s.run_pt(meta['T'])
+    assert out['sampled_params'].shape == z['sampled_params'].shape             # (N, 2 niter, d)
+    np.testing.assert_array_equal(out['swaps'][:, :2], z['pairs'])                # the chains proposed for a swap
+    ref_swapped = np.any(z['sampled_params'][:, 0::2] != z['sampled_params'][:, 1::2], axis=(0, 2))
+    got_swapped = np.any(out['sampled_params'][:, 0::2] != out['sampled_params'][:, 1::2], axis=(0, 2))
+    np.testing.assert_array_equal(got_swapped, ref_swapped)
+    assert ref_swapped.sum() > 3 and (~ref_swapped).sum() > 3
+    # accept / reject sequence of the steps: state changed between the post-swap row of t-1 and the step row of t
+    ref_sp, got_sp = z['sampled_params'], out['sampled_params']
+    ref_acc = np.any(ref_sp[:, 2::2] != ref_sp[:, 1:-1:2], axis=2)
+    np.testing.assert_array_equal(np.any(got_sp[:, 2::2] != got_sp[:, 1:-1:2], axis=2), ref_acc)
+    np.testing.assert_array_equal((out['decisions'][:, 2::2] & 1).astype(bool), ref_acc)
+    np.testing.assert_allclose(got_sp, ref_sp, rtol=1e-10, atol=1e-11)
+    ref_lp = z['log_ps'][:, :, 0]
+    assert np.all(np.abs(out['log_ps'] - ref_lp) <= logp_tol(ref_lp)), np.abs(out['log_ps'] - ref_lp).max()
+    hf = s.history_flat
+    assert hf.shape == z['history_final'].shape
+    np.testing.assert_allclose(hf, z['history_final'], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(s.cr_probs, z['cr_probs'][-1], rtol=1e-12)
 
 
 def test_oracle_threads_identical():
