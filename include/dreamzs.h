@@ -151,6 +151,28 @@ int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state *st, void *
 int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                  int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream);
 
+/* Parallel tempering (_sample_dream_pt, pydream/core.py:131-236; run_dream(..., tempering=True)).  One iteration
+ * of the driver is
+ *   dreamzs_step_tempered : Dream.astep(q0, T, last_loglike, last_logprior) (Dream.py:193) for every local chain
+ *                           at temperature[c] (nchains_local doubles, device): every log-posterior of the step is
+ *                           T * log_like + log_prior (Dream.py:243, 268, 274, 279, 303, 899), last_like / last_prior
+ *                           stay untempered (Dream.py:345-347) and trace_logp receives T * like + prior (core.py:176).
+ *                           Writes trace row tr->trace_offset; appends when iter % history_thin == 0.
+ *   dreamzs_pt_swap       : the proposed exchange of core.py:183-225.  The driver's draws come from the stream of the
+ *                           pseudo-chain 0xFFFFFFFF: the pair (first, second) by the random.sample contract
+ *                           (np.random.choice(nchains, 2, replace=False), core.py:183), then one 53-bit uniform
+ *                           (core.py:195); alpha = (T1 l2 + T2 l1) - (T1 l1 + T2 l2); when log(u) < alpha the two
+ *                           chains exchange state, last_like and last_prior.  Every chain is then recorded again in
+ *                           trace row tr->trace_offset (row trace_offset - 1 must hold the step's record; trace_logp
+ *                           travels with the state, decisions get DREAMZS_DECISION_SWAPPED for the two chains).
+ *                           swap_ws: 8 doubles of device scratch, left as (first, second, accepted, alpha, ...).
+ *                           All chains must be local (the pair may be any two chains).
+ * A tempered run therefore holds 2 trace rows per iteration, as the reference returns them (core.py:145-146). */
+int dreamzs_step_tempered(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
+                          int64_t iter, int64_t archive_rows, const double *temperature, void *stream);
+int dreamzs_pt_swap(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter,
+                    const double *temperature, double *swap_ws, void *stream);
+
 /* Split step for likelihoods the caller evaluates (Model.total_logp calls the user's likelihood, pydream/model.py:30;
  * target_kind DREAMZS_TARGET_EXTERNAL).  Without multi-try one iteration of every local chain is
  *   dreamzs_propose : decisions, archive gather, DE / snooker proposal, crossover, boundary handling, log prior

@@ -17,9 +17,10 @@ FLAG_ALL_FLAT = 1
 FLAG_GENERIC_KERNEL = 2
 FLAG_NO_WINDOW_KERNEL = 4
 PRIOR_FLAT, PRIOR_NORMAL, PRIOR_UNIFORM = 0, 1, 2
+DECISION_SWAPPED = 1 << 20
 
 EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_run', 'dreamzs_copy_d2h_2d',
-           'dreamzs_propose', 'dreamzs_select', 'dreamzs_accept',
+           'dreamzs_propose', 'dreamzs_select', 'dreamzs_accept', 'dreamzs_step_tempered', 'dreamzs_pt_swap',
            'dreamzs_shared_alloc', 'dreamzs_shared_open', 'dreamzs_shared_close', 'dreamzs_shared_free', 'dreamzs_adapt_workspace_bytes',
            'dreamzs_adapt_colsum', 'dreamzs_adapt_colsq', 'dreamzs_adapt_jumps', 'dreamzs_adapt_finish',
            'dreamzs_gr_chain_stats', 'dreamzs_gr_finish']
@@ -98,6 +99,8 @@ def load():
         'dreamzs_propose': (C.c_int, [cfgp, stp, i64, i64, vp, vp, vp]),
         'dreamzs_select': (C.c_int, [cfgp, stp, i64, i64, vp, vp, vp, vp, vp]),
         'dreamzs_accept': (C.c_int, [cfgp, stp, trp, i64, i64, vp, vp, vp, vp]),
+        'dreamzs_step_tempered': (C.c_int, [cfgp, stp, trp, i64, i64, vp, vp]),
+        'dreamzs_pt_swap': (C.c_int, [cfgp, stp, trp, i64, vp, vp, vp]),
         'dreamzs_adapt_workspace_bytes': (i64, [cfgp]),
         'dreamzs_adapt_colsum': (C.c_int, [cfgp, vp, vp, vp, vp]),
         'dreamzs_adapt_colsq': (C.c_int, [cfgp, vp, vp, vp, vp, vp]),

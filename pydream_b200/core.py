@@ -75,9 +75,6 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
                               verbose=verbose, mp_context=mp_context, **kwargs)
     else:
         step_instance = Dream(model=model, variables=parameters, verbose=verbose, mp_context=mp_context, **kwargs)
-    if tempering:
-        raise NotImplementedError('parallel tempering (pydream/core.py:131-248, "untested" in the reference) is outside '
-                                  'the accelerated step path')
 
     d = step_instance.total_var_dimension
     # ---- checks and sizing of _setup_mp_dream_pool (pydream/core.py:250-305), same messages
@@ -148,7 +145,12 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
     on_chunk = None
     if verbose:
         on_chunk = lambda dec, t0: acc_chunks.append((dec & 1).to(torch.float64).mean(dim=0))
-    if return_device:
+    if tempering:
+        # _sample_dream_pt (pydream/core.py:131-236): two records per iteration (after the step, after the swap)
+        trace, logp, dec, swaps = eng.run_tempered(niterations)
+        if verbose:
+            _print_tempering(dec, swaps, niterations, nchains)
+    elif return_device:
         trace, logp, dec = eng.run(niterations)
         if verbose and dec is not None:
             on_chunk(dec, 0)
@@ -175,6 +177,12 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
     if return_device:
         eng.check_peers()
         return trace, logp     # (a sharded caller keeps `trace` alive; the shared archive is released with the engine)
+    if tempering:
+        # arrays (nchains, 2 niterations, ndim) and (nchains, 2 niterations, 1), as core.py:145-146, 236
+        sampled_params = trace[:, :, :d].contiguous().cpu().numpy()
+        log_ps = logp.unsqueeze(2).cpu().numpy()
+        eng.close()
+        return sampled_params, log_ps
     torch.cuda.current_stream(eng.device).synchronize()
     eng.check_peers()
     eng.close()
@@ -186,6 +194,19 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
         print('run_dream stages (ms): engine+upload %.2f, enqueue %.2f, drain %.2f, lists %.2f'
               % (1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (t_d - t_c), 1e3 * (time.perf_counter() - t_d)))
     return sampled_params, log_ps
+
+
+def _print_tempering(dec, swaps, niterations, nchains):
+    """The progress lines of _sample_dream_pt (pydream/core.py:159-171) every 10 iterations, from the decision words:
+    per-chain acceptance rate of the steps and the rate of accepted temperature swaps."""
+    import torch
+    acc = torch.cumsum((dec[:, 0::2] & 1).to(torch.float64), dim=1).cpu().numpy()          # [N, niter]
+    sw = torch.cumsum(swaps[:, 2], dim=0).cpu().numpy()
+    for iteration in range(0, niterations, 10):
+        naccepts = acc[:, iteration - 1] if iteration > 0 else np.zeros(nchains)
+        nswaps = sw[iteration - 1] if iteration > 0 else 0.0
+        print('Iteration: ', iteration, ' overall acceptance rate: ', naccepts/(iteration/float(nchains) + iteration + 1),
+              ' and overall temp swap acceptance rate: ', nswaps/(iteration+1))
 
 
 def _print_acceptance(acc_mean, niterations, nverbose):

@@ -123,16 +123,24 @@ extern "C" int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state 
 
 static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter_begin,
                      int32_t niter, int64_t archive_rows, const dreamzs_peers *peers, uint64_t wait_k, uint64_t publish_k,
-                     void *stream);
+                     void *stream, const double *temperature = nullptr);
 
 extern "C" int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                             int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream) {
   return step_impl(cfg, st, tr, iter_begin, niter, archive_rows, nullptr, 0, 0, stream);
 }
 
+// astep(q0, T, last_loglike, last_logprior) at per-chain temperatures (Dream.py:193; the tempering driver calls it
+// once per chain and iteration, core.py:173, 232): one iteration on the generic kernel, which carries T.
+extern "C" int dreamzs_step_tempered(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
+                                     int64_t iter, int64_t archive_rows, const double *temperature, void *stream) {
+  if (!temperature) return DREAMZS_E_BADARG;
+  return step_impl(cfg, st, tr, iter, 1, archive_rows, nullptr, 0, 0, stream, temperature);
+}
+
 static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter_begin,
                      int32_t niter, int64_t archive_rows, const dreamzs_peers *peers, uint64_t wait_k, uint64_t publish_k,
-                     void *stream) {
+                     void *stream, const double *temperature) {
   int rc = check_cfg(cfg, st);
   if (rc != DREAMZS_OK) return rc;
   if (cfg->target_kind == DREAMZS_TARGET_EXTERNAL) return DREAMZS_E_UNSUPPORTED;   // use dreamzs_propose / dreamzs_accept
@@ -149,6 +157,11 @@ static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const d
   StepParams P{};
   P.cfg = *cfg; P.st = *st; P.tr = *tr; P.iter_begin = iter_begin; P.niter = niter; P.archive_rows = archive_rows;
   P.all_flat = all_flat_hint(cfg);
+  if (temperature) {   // only the generic kernel scales the log-likelihood; the dense-Gaussian kernels assume T = 1
+    P.temperature = temperature;
+    P.cfg.flags |= DREAMZS_FLAG_GENERIC_KERNEL;
+    P.st.gauss_Y = nullptr; P.st.gauss_Q = nullptr;
+  }
   if (peers) {
     if (peers->world < 1 || peers->world > DREAMZS_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) return DREAMZS_E_BADARG;
     for (int q = 0; q < peers->world; ++q)

@@ -517,6 +517,8 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
     return;
   }
   double last_prior = P.st.last_prior[c_local], last_like = P.st.last_like[c_local];
+  // temperature of astep(q0, T, ...): log_ps = T * log_like + log_prior everywhere (Dream.py:243, 268, 274, 279, 303, 899)
+  const double Tc = P.temperature ? P.temperature[c_local] : 1.0;
 
   double crp[DREAMZS_MAX_NCR], gp[DREAMZS_MAX_NGAMMA];
   for (int j = 0; j < P.cfg.nCR; ++j) crp[j] = P.st.cr_probs[j];
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
     }
     dc.lvl_idx = multinomial_index(s, gp, P.cfg.ngamma);                               // set_gamma_level, :585-599
 
-    const double last_logp = 1.0 * last_like + last_prior;
+    const double last_logp = Tc * last_like + last_prior;
     double D0 = 0.0;
     bool accepted = false, gamma_one;
     int sel = 0;
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
           return;
         }
       }
-      const double q_logp = 1.0 * q_like + q_prior;
+      const double q_logp = Tc * q_like + q_prior;
       double mr;
       if (dc.run_snooker) {                                                            // Dream.py:326-332
         const double norm = sqrt(D0);
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
           gamma_one = gen_eval_batch_mt<G, R>(c, s, dc, k, M, x0, 0, false, pri, lik, snk, D0);
           if (P.ext_phase == 1) break;
           bool anyfinite = false;
-          for (int p = 0; p < k; ++p) anyfinite |= isfinite(1.0 * lik[p] + pri[p]);
+          for (int p = 0; p < k; ++p) anyfinite |= isfinite(Tc * lik[p] + pri[p]);
           if (anyfinite || guard >= 1000) break;
         }
         if (P.ext_phase == 1) {   // hand the k proposals to the caller
@@ -626,16 +628,16 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
         s.n_rand = (uint32_t)ax[2 * k];
         if (P.ext_phase == 2) {   // the regenerate loop of Dream.py:282-289 needs new draws: not available in the split step
           bool anyfinite = false;
-          for (int p = 0; p < k; ++p) anyfinite |= isfinite(1.0 * lik[p] + pri[p]);
+          for (int p = 0; p < k; ++p) anyfinite |= isfinite(Tc * lik[p] + pri[p]);
           if (!anyfinite && c.g == 0) atomicExch(P.ext_error, 1);
         }
       }
       if (P.ext_phase <= 2) {
         // mt_choose_proposal_pt, Dream.py:883-917
-        double mx = 1.0 * lik[0] + pri[0];
-        for (int p = 1; p < k; ++p) { const double v = 1.0 * lik[p] + pri[p]; if (v > mx) mx = v; }
+        double mx = Tc * lik[0] + pri[0];
+        for (int p = 1; p < k; ++p) { const double v = Tc * lik[p] + pri[p]; if (v > mx) mx = v; }
         double prob[DREAMZS_MAX_MULTITRY], sum = 0.0;
-        for (int p = 0; p < k; ++p) { prob[p] = exp((1.0 * lik[p] + pri[p]) - mx); sum = (p == 0) ? prob[0] : sum + prob[p]; }
+        for (int p = 0; p < k; ++p) { prob[p] = exp((Tc * lik[p] + pri[p]) - mx); sum = (p == 0) ? prob[0] : sum + prob[p]; }
         for (int p = 0; p < k; ++p) prob[p] = prob[p] / sum;
         sel = multinomial_index(s, prob, k);
       } else {
@@ -682,9 +684,9 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
       double tp[DREAMZS_MAX_MULTITRY], trf[DREAMZS_MAX_MULTITRY];
       double m2 = -INFINITY;
       for (int p = 0; p < k; ++p) {
-        const double lps = 1.0 * lik[p] + pri[p];
+        const double lps = Tc * lik[p] + pri[p];
         const double rl = (p == k - 1) ? last_like : rlik[p], rp = (p == k - 1) ? last_prior : rpri[p];
-        const double rlps = 1.0 * rl + rp;
+        const double rlps = Tc * rl + rp;
         if (dc.run_snooker) {                                                          // Dream.py:306-313
           const double rs = (p == k - 1) ? 0.0 : rsnk[p];
           tp[p] = lps + snk[p]; trf[p] = rlps + rs + snk[p];
@@ -716,7 +718,7 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
     const int64_t trow = P.tr.trace_offset + it;
     store_row<G, R>(c, P.tr.trace + ((size_t)c_local * P.tr.trace_iters + trow) * ld, x0);
     if (c.g == 0) {
-      P.tr.trace_logp[(size_t)c_local * P.tr.trace_iters + trow] = last_like + last_prior;
+      P.tr.trace_logp[(size_t)c_local * P.tr.trace_iters + trow] = Tc * last_like + last_prior;   // core.py:115 (T = 1), :176
       if (P.tr.decisions)
         P.tr.decisions[(size_t)c_local * P.tr.trace_iters + trow] =
             pack_decision(changed, dc.run_snooker, dc.cr_idx, dc.lvl_idx, dc.delta, sel, gamma_one, accepted);

@@ -34,6 +34,7 @@ struct StepParams {
   long long *dbg;         // optional phase-timestamp buffer (dreamzs_debug_set_phase_buffer; profiling aid)
   int32_t gw_append;      // window kernel: the last iteration of the launch appends to the archive
   int32_t gw_refresh;     // window kernel: re-derive gauss_Y / gauss_Q from X at the start of the launch
+  const double *temperature;   // [nchains_local] per-chain temperature T of astep(q0, T, ...) (Dream.py:193); NULL = 1
 };
 
 }  // namespace dreamzs

@@ -62,6 +62,14 @@ def device_target_table(target, ld):
     return np.ascontiguousarray(target.table(), dtype=np.float64)
 
 
+def temperature_ladder(nchains):
+    """T[i] = 0.001 ** (i / nchains): the ladder of _sample_dream_pt (pydream/core.py:133-136)."""
+    T_ = np.zeros((nchains))
+    for i in range(nchains):
+        T_[i] = np.power(.001, (float(i) / nchains))
+    return T_
+
+
 def appends_in(iter_begin, niter, thin):
     """Number of iterations t in [iter_begin, iter_begin+niter) with t % thin == 0."""
     if niter <= 0:
@@ -404,24 +412,80 @@ class DreamEngine:
             if adapting and ((10 < t < self.crossover_burnin) or t == self.crossover_burnin):
                 trow, T_ = t - t_first, trace.shape[1]
                 x_old, ld_old = (p(x_entry), self.ld) if trow == 0 else (C.c_void_p(trace.data_ptr() + (trow - 1) * self.ld * 8), T_ * self.ld)
-                dec = C.c_void_p(decisions.data_ptr() + trow * 4)
-                _cabi.check(lib.dreamzs_adapt_colsum(cfg, p(self.X), p(self.colsum), p(self.workspace), stream), 'dreamzs_adapt_colsum')
-                allreduce_sum(self.colsum, self.group)
-                _cabi.check(lib.dreamzs_adapt_colsq(cfg, p(self.X), p(self.colsum), p(self.colsq), p(self.workspace), stream), 'dreamzs_adapt_colsq')
-                allreduce_sum(self.colsq, self.group)
-                _cabi.check(lib.dreamzs_adapt_jumps(cfg, p(self.X), x_old, ld_old, dec, T_, p(self.colsq), int(t == self.crossover_burnin),
-                                                    int(self.adapt_crossover), int(self.adapt_gamma), p(self.partial), p(self.workspace), stream),
-                            'dreamzs_adapt_jumps')
-                allreduce_sum(self.partial, self.group)
-                _cabi.check(lib.dreamzs_adapt_finish(cfg, p(self.partial), int(self.adapt_crossover), int(self.adapt_gamma),
-                                                     p(self.ncr_updates), p(self.delta_m), p(self.cr_probs), p(self.ngamma_updates),
-                                                     p(self.delta_m_gamma), p(self.gamma_probs), stream), 'dreamzs_adapt_finish')
-                self.launches += 7
+                self._adapt_stage(t, x_old, ld_old, C.c_void_p(decisions.data_ptr() + trow * 4), T_)
             if t % self.thin == 0:       # record_history for every chain; sharded: gather the other ranks' rows
                 M = self.archive_rows
                 allgather_rows(self.Z[M:M + self.N], self.c0, self.Nl, self.group)
                 self.count += self.N
         self.iter = t_first + niter
+
+    def _adapt_stage(self, t, x_old, ld_old, dec, dec_stride):
+        """One sweep of estimate_crossover_probabilities / estimate_gamma_level_probs (Dream.py:451-540) after
+        iteration t: x_old / ld_old = the states before the iteration (pointer, chain stride in doubles), dec /
+        dec_stride = this iteration's decision words."""
+        lib, cfg, stream = self.lib, C.byref(self.cfg), self._stream()
+        p = lambda x: C.c_void_p(x.data_ptr())
+        _cabi.check(lib.dreamzs_adapt_colsum(cfg, p(self.X), p(self.colsum), p(self.workspace), stream), 'dreamzs_adapt_colsum')
+        allreduce_sum(self.colsum, self.group)
+        _cabi.check(lib.dreamzs_adapt_colsq(cfg, p(self.X), p(self.colsum), p(self.colsq), p(self.workspace), stream), 'dreamzs_adapt_colsq')
+        allreduce_sum(self.colsq, self.group)
+        _cabi.check(lib.dreamzs_adapt_jumps(cfg, p(self.X), x_old, ld_old, dec, dec_stride, p(self.colsq), int(t == self.crossover_burnin),
+                                            int(self.adapt_crossover), int(self.adapt_gamma), p(self.partial), p(self.workspace), stream),
+                    'dreamzs_adapt_jumps')
+        allreduce_sum(self.partial, self.group)
+        _cabi.check(lib.dreamzs_adapt_finish(cfg, p(self.partial), int(self.adapt_crossover), int(self.adapt_gamma),
+                                             p(self.ncr_updates), p(self.delta_m), p(self.cr_probs), p(self.ngamma_updates),
+                                             p(self.delta_m_gamma), p(self.gamma_probs), stream), 'dreamzs_adapt_finish')
+        self.launches += 7
+
+    def run_tempered(self, niter, temperature=None):
+        """Parallel tempering, the loop of _sample_dream_pt (pydream/core.py:131-236): per iteration one astep of every
+        chain at its temperature (dreamzs_step_tempered; trace row 2t), the burn-in adaptation sweep if any, then the
+        proposed exchange between two chains (dreamzs_pt_swap; trace row 2t+1).  `temperature` defaults to the
+        reference's ladder T[i] = 0.001 ** (i / nchains).  Returns device tensors (trace [N, 2 niter, ld],
+        logp [N, 2 niter] = T like + prior, decisions [N, 2 niter], swaps [niter, 4] = first chain, second chain,
+        accepted, alpha).  All chains must live on this GPU (the exchanged pair may be any two chains)."""
+        if self.world > 1:
+            raise NotImplementedError('parallel tempering exchanges states between arbitrary chains: run it on one GPU')
+        if self.external:
+            raise NotImplementedError('parallel tempering needs an analytic target (the split step carries no temperature)')
+        niter = int(niter)
+        dev = self.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        if temperature is None:
+            temperature = temperature_ladder(self.N)
+        self.temperature = torch.as_tensor(np.ascontiguousarray(temperature, dtype=np.float64)).to(dev)
+        if self.temperature.numel() != self.N:
+            raise ValueError('one temperature per chain')
+        trace = torch.empty((self.Nl, 2 * niter, self.ld), **f64)
+        logp = torch.empty((self.Nl, 2 * niter), **f64)
+        decisions = torch.zeros((self.Nl, 2 * niter), dtype=torch.int32, device=dev)
+        swaps = torch.zeros((niter, 8), **f64)
+        self._ensure_capacity(self.archive_rows + appends_in(self.iter, niter, self.thin) * self.N)
+        lib, cfg, st, stream = self.lib, C.byref(self.cfg), C.byref(self.st), self._stream()
+        p = lambda x: C.c_void_p(x.data_ptr())
+        tr = _cabi.Trace(trace=trace.data_ptr(), trace_logp=logp.data_ptr(), decisions=decisions.data_ptr(),
+                         trace_iters=2 * niter, trace_offset=0)
+        adapting = self.adapt_crossover or self.adapt_gamma
+        t_first = self.iter
+        x_entry = self.X.clone() if adapting and t_first <= self.crossover_burnin else None
+        for t in range(t_first, t_first + niter):
+            row = 2 * (t - t_first)
+            tr.trace_offset = row
+            _cabi.check(lib.dreamzs_step_tempered(cfg, st, C.byref(tr), t, self.archive_rows, p(self.temperature), stream),
+                        'dreamzs_step_tempered')
+            self.launches += 1
+            if adapting and ((10 < t < self.crossover_burnin) or t == self.crossover_burnin):
+                # q0 of this astep is the state after the previous iteration's exchange (trace row 2t-1)
+                x_old, ld_old = (p(x_entry), self.ld) if row == 0 else (C.c_void_p(trace.data_ptr() + (row - 1) * self.ld * 8), 2 * niter * self.ld)
+                self._adapt_stage(t, x_old, ld_old, C.c_void_p(decisions.data_ptr() + row * 4), 2 * niter)
+            if t % self.thin == 0:
+                self.count += self.N
+            tr.trace_offset = row + 1
+            _cabi.check(lib.dreamzs_pt_swap(cfg, st, C.byref(tr), t, p(self.temperature), p(swaps[t - t_first]), stream), 'dreamzs_pt_swap')
+            self.launches += 2
+        self.iter = t_first + niter
+        return trace, logp, decisions, swaps[:, :4]
 
     def run_to_host(self, niter, out_params, out_logp, chunk_iters=256, on_chunk=None):
         """Run `niter` iterations and stream the samples to host memory while sampling continues.
