@@ -485,6 +485,11 @@ class DreamEngine:
             _cabi.check(lib.dreamzs_pt_swap(cfg, st, C.byref(tr), t, p(self.temperature), p(swaps[t - t_first]), stream), 'dreamzs_pt_swap')
             self.launches += 2
         self.iter = t_first + niter
+        if self.gauss_Y is not None:
+            # the window kernel's carried y = invC x / Q = x.y went stale (the tempered step does not maintain them):
+            # re-derive them (and, identically, last_prior / last_like) in case the engine continues untempered
+            _cabi.check(lib.dreamzs_init_logp(cfg, st, stream), 'dreamzs_init_logp')
+            self.launches += 1
         return trace, logp, decisions, swaps[:, :4]
 
     def run_to_host(self, niter, out_params, out_logp, chunk_iters=256, on_chunk=None):
