@@ -87,6 +87,13 @@ CASES = {
     'stdnorm10_defaults': dict(target=dict(kind='constant', d=10),
                                prior=dict(kind='norm', loc=[0.] * 10, scale=[1.] * 10), N=3, T=150, nseed=100,
                                seed=20, hist='prior_norm', kw=dict()),
+    # one-dimensional models (pydream/tests/test_dream.py onedmodel: nCR collapses to 1, no crossover adaptation,
+    # scalar boundary mask Dream.py:84-85)
+    'norm1_onedim': dict(target=dict(kind='sumshift', d=1), prior=dict(kind='norm', loc=[-2.], scale=[3.]), N=4, T=60,
+                         nseed=16, seed=41, hist='prior_norm',
+                         kw=dict(history_thin=2, crossover_burnin=20, nCR=1, adapt_crossover=False, snooker=.2)),
+    # (with one dimension the reference itself crashes under numpy 2 when multi-try is on -- np.squeeze leaves a 0-d
+    # q_proposal, Dream.py:723 -- and when a proposal leaves a finite boundary -- Dream.py:766: no golden case possible)
     'mixed5_nobounds': dict(target=dict(kind='constant', d=5),
                             prior=dict(kind='mixed', loc=[[0., 1.], [-1., -2., 0.]], scale=[[1., 2.], [2., 4., 1.]]),
                             N=4, T=80, nseed=16, seed=21, hist='mixed',
