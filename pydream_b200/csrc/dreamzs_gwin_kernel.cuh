@@ -36,7 +36,10 @@
 namespace dreamzs {
 
 constexpr int GW_THREADS = 512;
-constexpr int GW_GROUPS = 2;                               // independent warp groups per CTA
+#ifndef DZ_GW_GROUPS
+#define DZ_GW_GROUPS 2
+#endif
+constexpr int GW_GROUPS = DZ_GW_GROUPS;                    // independent warp groups per CTA (2 or 4; A/B builds override)
 constexpr int GW_GWARPS = GW_THREADS / 32 / GW_GROUPS;     // warps per group
 constexpr int GW_GTHREADS = GW_GWARPS * 32;
 constexpr int GW_KS = 2;       // K split of the products; fixed: the summation order is part of the result
