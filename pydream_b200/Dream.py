@@ -106,8 +106,9 @@ class Dream():
 
     def astep(self, q0, T=1., last_loglike=None, last_logprior=None):
         raise Exception('Dream should be run with multiple chains in parallel.  Set nchains > 1.  '
-                        '(pydream_b200 steps all chains at once on the GPU: use pydream_b200.core.run_dream '
-                        'or pydream_b200.engine.DreamEngine.run)')
+                        '(pydream_b200 steps all chains at once on the GPU: use pydream_b200.core.run_dream, '
+                        'pydream_b200.engine.DreamEngine.run, or DreamEngine.astep -- the same operator contract '
+                        'for every chain at once)')
 
     def save_history_to_disc(self, history, prefix):
         """Same three files and messages as pydream/Dream.py:947-969."""

@@ -419,6 +419,56 @@ class DreamEngine:
                 self.count += self.N
         self.iter = t_first + niter
 
+    def astep(self, q0=None, T=1., last_loglike=None, last_logprior=None):
+        """The step-operator contract of the reference, `Dream.astep(q0, T, last_loglike, last_logprior) ->
+        (q_new, log_prior, log_like)` (pydream/Dream.py:193, 422; called by name in core.py:97, 114 and 232), for every
+        local chain at once: one iteration (appends to the archive when iter % history_thin == 0, burn-in
+        adaptation included).  q0 [N_local, ndim] replaces the current positions (None: continue from them);
+        last_loglike / last_logprior [N_local] replace the stored values as in Dream.py:240-243 (None with a new q0:
+        they are re-evaluated, the first-call branch Dream.py:266-268); T is a scalar or one temperature per local
+        chain.  Returns device tensors (q_new [N_local, ndim], log_prior [N_local], log_like [N_local])."""
+        f64 = dict(dtype=torch.float64, device=self.device)
+        lib, cfg, stream = self.lib, C.byref(self.cfg), self._stream()
+        p = lambda x: C.c_void_p(x.data_ptr())
+        if self.external:
+            raise NotImplementedError('astep needs an analytic target; caller-evaluated likelihoods go through run()')
+        if q0 is not None:
+            self.X[:, :self.d] = torch.as_tensor(q0, **f64).reshape(self.Nl, self.d)
+            # first-call branch (also re-derives the window kernel's carried y = invC x, Q = x.y)
+            _cabi.check(lib.dreamzs_init_logp(cfg, C.byref(self.st), stream), 'dreamzs_init_logp')
+            self.launches += 1
+        if last_loglike is not None:
+            self.last_like.copy_(torch.as_tensor(last_loglike, **f64).reshape(self.Nl))
+            self.last_prior.copy_(torch.as_tensor(last_logprior, **f64).reshape(self.Nl))
+        trace = torch.empty((self.Nl, 1, self.ld), **f64)
+        logp = torch.empty((self.Nl, 1), **f64)
+        dec = torch.empty((self.Nl, 1), dtype=torch.int32, device=self.device)
+        t = self.iter
+        self._ensure_capacity(self.archive_rows + appends_in(t, 1, self.thin) * self.N)
+        Tt = torch.as_tensor(T, **f64)
+        if Tt.numel() == 1 and float(Tt) == 1.0:
+            self._advance(1, trace, logp, dec)          # fused kernels, sharded archives, adaptation
+        else:
+            if self.world > 1:
+                raise NotImplementedError('tempered steps run on one GPU')
+            self.temperature = Tt.expand(self.Nl).contiguous() if Tt.numel() == 1 else Tt.reshape(self.Nl).contiguous()
+            adapting = (self.adapt_crossover or self.adapt_gamma) and ((10 < t < self.crossover_burnin) or t == self.crossover_burnin)
+            x_entry = self.X.clone() if adapting else None
+            tr = _cabi.Trace(trace=trace.data_ptr(), trace_logp=logp.data_ptr(), decisions=dec.data_ptr(), trace_iters=1, trace_offset=0)
+            _cabi.check(lib.dreamzs_step_tempered(cfg, C.byref(self.st), C.byref(tr), t, self.archive_rows, p(self.temperature), stream),
+                        'dreamzs_step_tempered')
+            self.launches += 1
+            if adapting:
+                self._adapt_stage(t, p(x_entry), self.ld, p(dec), 1)
+            if t % self.thin == 0:
+                self.count += self.N
+            self.iter = t + 1
+            if self.gauss_Y is not None:    # keep the window kernel's carried state valid for an untempered continuation
+                _cabi.check(lib.dreamzs_init_logp(cfg, C.byref(self.st), stream), 'dreamzs_init_logp')
+                self.launches += 1
+        self.last_decisions = dec[:, 0]
+        return trace[:, 0, :self.d], self.last_prior.clone(), self.last_like.clone()
+
     def _adapt_stage(self, t, x_old, ld_old, dec, dec_stride):
         """One sweep of estimate_crossover_probabilities / estimate_gamma_level_probs (Dream.py:451-540) after
         iteration t: x_old / ld_old = the states before the iteration (pointer, chain stride in doubles), dec /

@@ -133,3 +133,41 @@ def test_run_dream_tempering_shapes_and_swaps(tmp_path, monkeypatch):
     assert nswaps > 0
     history = np.load('pt_DREAM_chain_history.npy')
     assert len(history) == 4 * (nchains * niter // 2 + 40)
+
+
+def test_astep_operator_contract():
+    """DreamEngine.astep(q0, T, last_loglike, last_logprior) -> (q_new, log_prior, log_like), the reference's step
+    operator (Dream.py:193, 422) for all chains at once: a loop over astep reproduces run(); passing the returned
+    state back in (as _sample_dream_pt_chain does, core.py:239-246) changes nothing; logp monotone on acceptance at
+    T = 1 without snooker (test_astep_*, pydream/tests/test_dream.py:499-562)."""
+    import torch
+    from pydream_b200.engine import DreamEngine
+    from pydream_b200 import targets
+    d, N, T = 100, 48, 14
+    rng = np.random.default_rng(6)
+    tgt = targets.CorrelatedGaussian.benchmark(d)
+    hist = rng.uniform(-5, 15, size=(3 * N, d))
+    kw = dict(seed=3, snooker=0., history_thin=5)
+    a = DreamEngine(d, N, hist, hist[:N], tgt, **kw)
+    tr_a, lp_a, dec_a = a.run(T)
+    b = DreamEngine(d, N, hist, hist[:N], tgt, **kw)
+    c = DreamEngine(d, N, hist, hist[:N], tgt, **kw)
+    q = lk = pr = None
+    for t in range(T):
+        q_b, pr_b, lk_b = b.astep()                                     # continue from the engine's own state
+        q, pr, lk = c.astep(q, 1., lk, pr) if q is not None else c.astep()   # state handed back in every call
+        assert q_b.shape == (N, d) and pr_b.shape == (N,) and lk_b.shape == (N,)
+        ref_lp = lp_a[:, t]
+        for qq, pp, ll in ((q_b, pr_b, lk_b), (q, pr, lk)):
+            np.testing.assert_allclose(qq.cpu().numpy(), tr_a[:, t, :d].cpu().numpy(), rtol=1e-10, atol=1e-11)
+            assert np.all(np.abs((ll + pp - ref_lp).cpu().numpy()) <= logp_tol(ref_lp.cpu().numpy()))
+        np.testing.assert_array_equal(b.last_decisions.cpu().numpy(), dec_a[:, t].cpu().numpy())
+        if t > 0:
+            acc = (dec_a[:, t] & 1).bool()
+            # accepted points were tested with log u < logp_new - logp_old; rejected ones keep their logp
+            assert torch.all(lp_a[:, t][~acc] == lp_a[:, t - 1][~acc])
+    assert b.archive_rows == a.archive_rows and b.iter == a.iter == T
+    # a tempered step through the same operator: T -> 0 flattens the likelihood, so (flat prior) every finite proposal is accepted
+    e = DreamEngine(d, N, hist, hist[:N], tgt, **kw)
+    q_e, pr_e, lk_e = e.astep(T=1e-300)
+    assert int((e.last_decisions & 1).sum()) >= N - 2
