@@ -20,6 +20,10 @@ def run_oracle(meta, z, nthreads=1):
 @pytest.mark.parametrize('name', golden_cases())
 def test_oracle_matches_reference(name):
     meta, z = load_case(name)
+    _check_against_reference(meta, z)
+
+
+def _check_against_reference(meta, z):
     s, out = run_oracle(meta, z)
     dec = decode_decisions(out['decisions'])
     # integer decisions: bit-exact
@@ -89,6 +93,81 @@ def test_oracle_matches_reference_tempering(name):
     assert hf.shape == z['history_final'].shape
     np.testing.assert_allclose(hf, z['history_final'], rtol=1e-10, atol=1e-11)
     np.testing.assert_allclose(s.cr_probs, z['cr_probs'][-1], rtol=1e-12)
+
+
+def _random_case(i):
+    """A small random configuration inside what the reference itself supports (niterations a multiple of
+    history_thin: its archive overflows otherwise, Dream.py:936; no multi-try in one dimension)."""
+    rng = np.random.default_rng(1000 + i)
+    kind = ['gaussian', 'banana', 'mixture', 'sumshift'][i % 4]
+    d = int(rng.integers(2, 13))
+    DEpairs = int(rng.integers(1, 3))
+    N = int(rng.integers(2 * DEpairs + 1, 2 * DEpairs + 5))
+    thin = int(rng.integers(1, 5))
+    T = thin * int(rng.integers(4, 9))
+    kw = dict(snooker=float(rng.choice([0., .1, .5])), history_thin=thin, DEpairs=DEpairs,
+              multitry=[False, False, 3, 5][int(rng.integers(0, 4))],   # (1 == True means 5 in the reference)
+               nCR=int(rng.integers(1, min(d, 4) + 1)), adapt_crossover=False,
+              crossover_burnin=3, p_gamma_unity=float(rng.choice([.2, .5])), gamma_levels=int(rng.integers(1, 4)))
+    if kind == 'sumshift':
+        prior = dict(kind='uniform', loc=[-4.] * d, scale=[9.] * d)
+        hist = -4. + 9. * rng.uniform(size=(2 * DEpairs * N + 6, d))
+        kw['lamb'] = .4
+    else:
+        prior = dict(kind='flat', d=d)
+        hist = rng.normal(size=(2 * DEpairs * N + 6, d)) * (3. if kind != 'mixture' else 1.)
+    return dict(target=dict(kind=kind, d=d), prior=prior, N=N, T=T, seed=500 + i, kw=kw), hist
+
+
+@pytest.mark.parametrize('i', range(16))
+def test_oracle_matches_live_reference(i):
+    """Fresh random cases through the UNMODIFIED reference (lock-step harness) and the C restatement, side by side.
+    Runs where /root/reference exists (the build container); the committed golden vectors cover the GPU box."""
+    from oracle import ref_harness as H
+    if not H.reference_available():
+        pytest.skip('reference checkout not present')
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden as G
+    meta, hist = _random_case(i)
+    starts = hist[:meta['N']].copy()
+    z = H.run_lockstep(G.make_params(meta['prior']), make_target(meta['target']), meta['N'], meta['T'], starts, hist,
+                       seed=meta['seed'], **meta['kw'])
+    z = dict(z, history=hist, starts=starts)
+    _check_against_reference(meta, z)
+
+
+@pytest.mark.parametrize('i', range(6))
+def test_oracle_matches_live_reference_tempering(i):
+    """The same for parallel tempering: the reference's _sample_dream_pt on the lock-step pool vs dreamzs_oracle_run_pt."""
+    from oracle import ref_harness as H
+    if not H.reference_available():
+        pytest.skip('reference checkout not present')
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden as G
+    meta, hist = _random_case(100 + i)
+    d, N = meta['target']['d'], meta['N']
+    starts = hist[:N].copy()
+    z = H.run_lockstep_pt(G.make_params(meta['prior']), make_target(meta['target']), N, meta['T'], starts, hist,
+                          seed=meta['seed'], **meta['kw'])
+    tgt = make_target(meta['target'])
+    pk, pa, pb = prior_arrays(meta['prior'], d)
+    s = c_oracle.OracleSampler(d, N, hist, starts, tgt.kind, tgt.table(), seed=meta['seed'], prior_kind=pk, prior_a=pa,
+                               prior_b=pb, **sampler_kwargs(meta))
+    out = s.run_pt(meta['T'])
+    np.testing.assert_array_equal(out['swaps'][:, :2], z['pairs'])
+    ref_sp, got_sp = z['sampled_params'], out['sampled_params']
+    np.testing.assert_array_equal(np.any(got_sp[:, 0::2] != got_sp[:, 1::2], axis=(0, 2)),
+                                  np.any(ref_sp[:, 0::2] != ref_sp[:, 1::2], axis=(0, 2)))
+    np.testing.assert_array_equal(np.any(got_sp[:, 2::2] != got_sp[:, 1:-1:2], axis=2),
+                                  np.any(ref_sp[:, 2::2] != ref_sp[:, 1:-1:2], axis=2))
+    np.testing.assert_allclose(got_sp, ref_sp, rtol=1e-10, atol=1e-11)
+    ref_lp = z['log_ps'][:, :, 0]
+    assert np.all(np.abs(out['log_ps'] - ref_lp) <= logp_tol(ref_lp)), np.abs(out['log_ps'] - ref_lp).max()
+    np.testing.assert_allclose(s.history_flat, z['history_final'], rtol=1e-10, atol=1e-11)
 
 
 def test_oracle_threads_identical():
