@@ -40,6 +40,12 @@ constexpr int GW_THREADS = 512;
 #define DZ_GW_GROUPS 2
 #endif
 constexpr int GW_GROUPS = DZ_GW_GROUPS;                    // independent warp groups per CTA (2 or 4; A/B builds override)
+// A/B builds only (default 0 = off): the odd groups run a short first batch of DZ_GW_STAGGER iterations, so that from
+// then on the groups of a CTA are out of phase (one group's latency-bound C next to the other's issue-bound G / M;
+// DESIGN.md section 9).  Results do not depend on how a launch is cut into batches.
+#ifndef DZ_GW_STAGGER
+#define DZ_GW_STAGGER 0
+#endif
 constexpr int GW_GWARPS = GW_THREADS / 32 / GW_GROUPS;     // warps per group
 constexpr int GW_GTHREADS = GW_GWARPS * 32;
 constexpr int GW_KS = 2;       // K split of the products; fixed: the summation order is part of the result
@@ -170,10 +176,20 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
   const int jl = ((d2 / 2 + GW_KS - 1) / GW_KS) * 2;       // K range of a split (even)
 
   int done = 0;
+#if DZ_GW_STAGGER > 0
+  uint32_t colphase = 0;   // bit k: mbarrier phase of this warp's k-th column (a column skipped by a short batch keeps its phase)
+#endif
   for (int batch = 0; done < P.niter; ++batch) {
+#if DZ_GW_STAGGER > 0
+    int nb = min(NB, P.niter - done);
+    if ((gid & 1) && batch == 0 && P.niter > DZ_GW_STAGGER) nb = min(nb, DZ_GW_STAGGER);
+#else
     const int nb = min(NB, P.niter - done);
+#endif
     const bool do_refresh = P.gw_refresh && batch == 0;
+#if DZ_GW_STAGGER == 0
     const uint32_t parity = (uint32_t)(batch & 1);
+#endif
     // ================================================================ G: generation (warp per column)
     // group-local column index cl = chain * NB + iteration; the warp owns cl = gw, gw + 8, gw + 16
     {
@@ -252,6 +268,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
         const uint32_t iter = (uint32_t)(P.iter_begin + done + itb);
         const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + gfirst + ch);
         const uint32_t mt = meta[col];
+#if DZ_GW_STAGGER > 0
+        const uint32_t parity = (colphase >> k) & 1u;
+        colphase ^= 1u << k;
+#endif
         const int snk = (mt >> 8) & 1, cr_idx = mt & 15, lvl_idx = (mt >> 4) & 15;
         double *js = Jc + (size_t)col * ld + i0, *zs = Zc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
         if (!snk) {
