@@ -87,8 +87,12 @@ class OracleSampler:
                  DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12, history_thin=10,
                  hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
                  prior_kind=None, prior_a=None, prior_b=None, capacity_rows=None, cr_probs=None, gamma_probs=None,
-                 nthreads=1):
+                 nthreads=1, chain_begin=0, nchains_global=None):
+        """nchains / starts describe the chains stepped HERE; a shard passes chain_begin and nchains_global (SURVEY.md
+        8(e): global chain ids in the random streams, archive row of an append = rows so far + global chain id) and
+        fetches the other shards' appended rows itself after every appending iteration (Z is exposed)."""
         d, N = int(ndim), int(nchains)
+        self.Ng = int(nchains_global) if nchains_global is not None else N
         self.d, self.N, self.ld = d, N, round_up4(d)
         history = np.asarray(history, dtype=np.float64).reshape(-1, d)
         self.nseed = history.shape[0]
@@ -100,7 +104,7 @@ class OracleSampler:
         self.last_prior, self.last_like = np.zeros(N), np.zeros(N)
         self.count = C.c_int64(0)
         self.nthreads = int(nthreads)
-        self.cfg = Config(abi_version=ABI_VERSION, ndim=d, ld=self.ld, nchains_global=N, chain_begin=0, nchains_local=N,
+        self.cfg = Config(abi_version=ABI_VERSION, ndim=d, ld=self.ld, nchains_global=self.Ng, chain_begin=int(chain_begin), nchains_local=N,
                           nCR=nCR, ngamma=gamma_levels, nDEpairs=DEpairs, multitry=multitry,
                           hardboundaries=int(bool(hardboundaries)), history_thin=history_thin,
                           target_kind=int(target_kind), snooker=snooker, p_gamma_unity=p_gamma_unity, lamb=lamb,
@@ -135,7 +139,7 @@ class OracleSampler:
     def ensure_capacity(self, niter):
         thin = self.cfg.history_thin
         appends = sum(1 for t in range(self.iter, self.iter + niter) if t % thin == 0)
-        need = self.nseed + self.count.value + appends * self.N
+        need = self.nseed + self.count.value + appends * self.Ng
         if need > self.Z.shape[0]:
             Z = np.zeros((need, self.ld))
             Z[:self.Z.shape[0]] = self.Z

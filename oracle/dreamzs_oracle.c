@@ -530,6 +530,8 @@ static int run_impl(const dreamzs_config *cfg, const dreamzs_state *st, dreamzs_
   if (cfg->abi_version != DREAMZS_ABI_VERSION || cfg->multitry < 1 || cfg->multitry > DREAMZS_MAX_MULTITRY ||
       cfg->multitry == 2 || cfg->nDEpairs > DREAMZS_MAX_DEPAIRS || cfg->nCR > DREAMZS_MAX_NCR)
     return DREAMZS_E_BADARG;
+  /* a shard (nchains_local < nchains_global) steps its own chains only; adaptation sums would need the other shards */
+  if (N != cfg->nchains_global && (ad->adapt_crossover || ad->adapt_gamma)) return DREAMZS_E_UNSUPPORTED;
   if (nthreads < 1) nthreads = 1;
   if (nthreads > N) nthreads = N;
   pool_t pl; memset(&pl, 0, sizeof(pl));
@@ -551,7 +553,7 @@ static int run_impl(const dreamzs_config *cfg, const dreamzs_state *st, dreamzs_
   for (int64_t it = 0; it < niter && rc == DREAMZS_OK; ++it) {
     const int64_t iter = iter_begin + it, M = nseed + *count;
     const int appends = iter % cfg->history_thin == 0;
-    if ((size_t)(M + (appends ? N : 0)) > (size_t)st->Z_capacity_rows) { rc = DREAMZS_E_BADARG; break; }
+    if ((size_t)(M + (appends ? cfg->nchains_global : 0)) > (size_t)st->Z_capacity_rows) { rc = DREAMZS_E_BADARG; break; }
     memcpy(pl.crp, ad->cr_probs, sizeof(double) * cfg->nCR);
     memcpy(pl.gp, ad->gamma_probs, sizeof(double) * cfg->ngamma);
     pl.iter = iter; pl.it = it; pl.M = M;
@@ -566,9 +568,10 @@ static int run_impl(const dreamzs_config *cfg, const dreamzs_state *st, dreamzs_
       trace_logp[(size_t)c * TR + it * rpi] = Tc * st->last_like[c] + st->last_prior[c];   /* core.py:115; :178 under tempering */
       if (decisions) decisions[(size_t)c * TR + it * rpi] = pl.dec[c];
     }
-    if (appends) {   /* record_history, Dream.py:360-362, 919-938 */
-      for (int c = 0; c < N; ++c) memcpy(st->Z + (size_t)(M + c) * ld, pl.Xnew + (size_t)c * ld, sizeof(double) * ld);
-      *count += N;
+    if (appends) {   /* record_history, Dream.py:360-362, 919-938: chain c's row is M + (global chain id) */
+      for (int c = 0; c < N; ++c)
+        memcpy(st->Z + (size_t)(M + cfg->chain_begin + c) * ld, pl.Xnew + (size_t)c * ld, sizeof(double) * ld);
+      *count += cfg->nchains_global;   /* a shard's caller fetches the other shards' rows before the next sweep */
     }
     if (temperature) {
       /* temperature swap of _sample_dream_pt (pydream/core.py:183-218): the parent process draws a pair of
