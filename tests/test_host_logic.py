@@ -176,3 +176,79 @@ def test_appends_in_matches_the_schedule():
         assert sum(m for _, m in segs) == n
         assert sum(1 for t, m in segs if (t + m - 1) % thin == 0) == appends_in(t0, n, thin)
         assert all((t + i) % thin != 0 for t, m in segs for i in range(m - 1))      # only a launch's last iteration appends
+
+
+def test_run_dream_host_path_reaches_engine(monkeypatch):
+    """Everything run_dream does on the host before the first launch (option validation, archive seed from the priors or
+    from history_file, start positions, defaults such as crossover_burnin = niterations/10), observed at the engine's
+    constructor (no GPU needed)."""
+    import pydream_b200.engine as E
+
+    class Reached(Exception):
+        pass
+
+    seen = {}
+
+    class FakeEngine:
+        def __init__(self, *a, **k):
+            seen['a'], seen['k'] = a, k
+            raise Reached()
+
+    monkeypatch.setattr(E, 'DreamEngine', FakeEngine)
+    param, like = multidmodel()
+    for kw, want in ((dict(), dict(multitry=1, DEpairs=1, gamma_levels=1, adapt_gamma=False)),
+                     (dict(tempering=True), dict(multitry=1)),
+                     (dict(multitry=True, DEpairs=2, gamma_levels=3, adapt_gamma=True), dict(multitry=5, DEpairs=2, gamma_levels=3, adapt_gamma=True)),
+                     (dict(hardboundaries=False, nCR=9), dict(hardboundaries=False, nCR=4))):
+        with pytest.raises(Reached):
+            run_dream(param, like, nchains=6, niterations=40, verbose=False, seed=1, **kw)
+        a, k = seen['a'], seen['k']
+        assert a[0] == 4 and a[1] == 6 and np.asarray(a[2]).shape == (40, 4) and np.asarray(a[3]).shape == (6, 4)
+        assert k['crossover_burnin'] == 4 and k['history_thin'] == 10 and k['seed'] == 1
+        for name, value in want.items():
+            assert k[name] == value, (name, k[name])
+        np.testing.assert_allclose(k['cr_probs'], np.full(k['nCR'], 1. / k['nCR']))
+    d = 12
+    hist = np.random.default_rng(0).uniform(-5, 15, size=(30, d))
+    with pytest.raises(Reached):      # the analytic examples' way: FlatParam + history_file + explicit starts
+        run_dream(FlatParam(test_value=np.zeros(d)), targets.CorrelatedGaussian.benchmark(d), nchains=5, niterations=20,
+                  start=[hist[c] for c in range(5)], start_random=False, history_file=hist, verbose=False, seed=0)
+    a, k = seen['a'], seen['k']
+    np.testing.assert_array_equal(np.asarray(a[2]), hist)
+    np.testing.assert_array_equal(np.asarray(a[3]), hist[:5])
+    with pytest.raises(Reached):      # one start array for every chain (core.py:77-78)
+        run_dream(FlatParam(test_value=np.zeros(d)), targets.CorrelatedGaussian.benchmark(d), nchains=5, niterations=20,
+                  start=hist[3], start_random=False, history_file=hist, verbose=False)
+    np.testing.assert_array_equal(np.asarray(seen['a'][3]), np.tile(hist[3], (5, 1)))
+
+
+def test_dream_option_set_matches_reference(capsys):
+    """Attributes and warning texts of pydream_b200.Dream against the reference's Dream.__init__ (pydream/Dream.py:63-191)
+    for a few option sets; runs where the reference checkout exists."""
+    import sys
+    if not os.path.isdir('/root/reference/pydream'):
+        pytest.skip('reference checkout not present')
+    sys.path.insert(0, '/root/reference')
+    import pydream.Dream as RD
+    import pydream.model as RM
+    import pydream.parameters as RP
+
+    def build(SP, M, D, kw):
+        params = [SP(norm, loc=np.arange(4.), scale=np.full(4, 1.5)), SP(uniform, loc=-1., scale=3.)]
+        capsys.readouterr()
+        obj = D(model=M(likelihood=lambda x: 0., sampled_parameters=params), **kw)
+        return obj, capsys.readouterr().out
+
+    for kw in (dict(), dict(nCR=9, gamma_levels=3, DEpairs=3, multitry=True, adapt_gamma=True, nseedchains=77, snooker=0, model_name='x'),
+               dict(multitry=1), dict(multitry=0), dict(multitry=4, zeta=1e-3, history_thin=3, crossover_burnin=17)):
+        r, rout = build(RP.SampledParam, RM.Model, RD.Dream, kw)
+        o, oout = build(SampledParam, Model, Dream, kw)
+        assert rout == oout
+        for name in ('total_var_dimension', 'nCR', 'ngamma', 'njoint_cr_gamma_probs', 'crossover_burnin', 'adapt_crossover',
+                     'adapt_gamma', 'snooker', 'p_gamma_unity', 'multitry', 'parallel', 'lamb', 'zeta', 'nseedchains',
+                     'history_thin', 'start_random', 'save_history', 'history_file', 'verbose', 'model_name', 'iter',
+                     'len_history', 'last_logp', 'gamma', 'chain_n', 'nchains', 'boundaries'):
+            assert np.all(getattr(r, name) == getattr(o, name)), name
+        for name in ('mins', 'maxs', 'CR_values', 'gamma_level_values', 'DEpairs', 'gamma_arr', 'CR_probabilities',
+                     'gamma_probabilities', 'boundary_mask'):
+            np.testing.assert_array_equal(np.asarray(getattr(r, name), dtype=float), np.asarray(getattr(o, name), dtype=float), err_msg=name)
