@@ -114,7 +114,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) dreamzs_gwin_kernel(const StepP
   const int gid = warp / GW_GWARPS, gw = warp - gid * GW_GWARPS;    // warp group, warp within the group
   const double logF = P.st.target_table[0];
   int dbg_n = 0;
+#if DZ_GW_STAGGER > 0   // A/B builds: also stamp warp 0 of the second group (entries 32..63), to see the phase offset
+#define GW_STAMP() do { if (P.dbg && blockIdx.x == 0 && (tid == 0 || tid == GW_GTHREADS)) P.dbg[(tid ? 32 : 0) + dbg_n] = clock64(); ++dbg_n; } while (0)
+#else
 #define GW_STAMP() do { if (P.dbg && blockIdx.x == 0 && tid == 0) P.dbg[dbg_n] = clock64(); ++dbg_n; } while (0)
+#endif
   GW_STAMP();   // 0: kernel entry
 
   const int i0 = 4 * lane;

@@ -60,9 +60,13 @@ def main():
 
     if a.phases:
         t = buf.cpu().numpy()
-        n = int((t != 0).sum())
+        n = int((t[:32] != 0).sum())
         print('phase stamps (cycles since kernel entry, CTA 0 thread 0):', [int(v - t[0]) for v in t[1:n]])
         print('deltas:', [int(t[i + 1] - t[i]) for i in range(n - 1)])
+        m = int((t[32:] != 0).sum())
+        if m:   # -DDZ_GW_STAGGER builds also stamp warp 0 of the second warp group
+            g = t[32:32 + m]
+            print('group 1 stamps (same origin):', [int(v - t[0]) for v in g])
 
 
 if __name__ == '__main__':
