@@ -37,7 +37,17 @@ import numpy as np
 
 from . import philox as px
 
-REF_ROOT = '/root/reference'
+def _find_reference():
+    """The unmodified reference: the checkout in the build container, else the copy installed (unchanged, by pip
+    --target) under baseline/_ref, which travels to the GPU box."""
+    inst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+    for root in ('/root/reference', inst):
+        if os.path.isdir(os.path.join(root, 'pydream')):
+            return root
+    return '/root/reference'
+
+
+REF_ROOT = _find_reference()
 
 
 class _Ctx:

@@ -102,12 +102,13 @@ class Dream():
         self.last_logp = self.gamma = self.chain_n = self.nchains = None
         self.iter = self.len_history = 0
 
-    def draw_from_prior(self, model_vars, random_seed=False):
-        """One draw from every prior, concatenated (pydream/Dream.py:628-644); same exception text."""
+    def draw_from_prior(self, model_vars, random_seed=False, rng=None):
+        """One draw from every prior, concatenated (pydream/Dream.py:628-644); same exception text.  `rng` (extension):
+        the numpy Generator run_dream derives from its `seed` keyword."""
         parts = []
         for variable in model_vars:
             try:      # FlatParam has no distribution to draw from: its `random` fails on the missing attribute
-                value = variable.random(reseed=random_seed)
+                value = variable.random(reseed=random_seed) if rng is None else variable.random(random_state=rng)
             except AttributeError:
                 raise Exception('Random draw from distribution for variable %s not implemented yet.' % variable)
             parts.append(np.asarray(value, dtype=np.float64).reshape(-1))

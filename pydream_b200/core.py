@@ -100,30 +100,46 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
             step_instance.start_random = False
 
     if not isinstance(likelihood, T.AnalyticTarget):
-        raise NotImplementedError(
-            'pydream_b200 runs the whole step on the GPU and needs a target from pydream_b200.targets: an analytic one '
-            '(CorrelatedGaussian, BimodalMixture, Banana, SumShift, Constant) or TorchLikelihood(ndim, fn) wrapping a '
-            'batched device callable; arbitrary Python likelihoods are not evaluated on the host (no CPU fallback)')
+        # the reference's contract, likelihood(param_vec) -> float (pydream/model.py:30): the step stays on the GPU
+        # (split into propose / select / accept), the user's function is called on the host for every proposal
+        if not callable(likelihood):
+            raise TypeError('likelihood must be a callable or a target from pydream_b200.targets')
+        likelihood = T.HostLikelihood(d, likelihood)
     if likelihood.ndim != d:
         raise ValueError('target dimension %d != total parameter dimension %d' % (likelihood.ndim, d))
     prior_kind, prior_a, prior_b = _prior_arrays(parameters)
 
+    # ---- seed of the run.  Everything random on the host side (archive seed, random starts) is drawn from a numpy
+    #      Philox generator keyed by it, the device side from the Philox contract of DESIGN.md keyed by it: a run with
+    #      `seed=` given is reproducible.  Sharded runs draw on rank 0 and broadcast, so every rank seeds the same
+    #      archive replica and the same chains as the single-GPU run.
+    sharded = group is not None and _world_size(group) > 1
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), 'little')
+        if sharded:
+            seed = _broadcast_from_rank0(seed, group)
+    seed = int(seed) & (2 ** 64 - 1)
+    host_rng = np.random.Generator(np.random.Philox(key=[seed, 0x5EED]))
+
     # ---- archive seed (Dream.py:203-214) and start positions (core.py:74-78, Dream.py:221-225)
+    drawn = None
     if old_history is not None:
         history = np.asarray(old_history, dtype=np.float64).reshape(-1, d)
     else:
         nseed = int(step_instance.nseedchains)
-        history = np.array([step_instance.draw_from_prior(step_instance.variables) for _ in range(nseed)]).reshape(nseed, d)
+        if not sharded or _rank(group) == 0:
+            drawn = np.array([step_instance.draw_from_prior(step_instance.variables, rng=host_rng) for _ in range(nseed)]).reshape(nseed, d)
+        history = _broadcast_from_rank0(drawn, group) if sharded else drawn
     if step_instance.start_random:
-        starts = np.array([step_instance.draw_from_prior(step_instance.variables, random_seed=True) for _ in range(nchains)])
+        drawn = None
+        if not sharded or _rank(group) == 0:
+            drawn = np.array([step_instance.draw_from_prior(step_instance.variables, random_seed=True, rng=host_rng) for _ in range(nchains)])
+        starts = _broadcast_from_rank0(drawn, group) if sharded else drawn
     elif type(start) is list:
         starts = np.array([np.asarray(s, dtype=np.float64).reshape(-1) for s in start[:nchains]])
     else:
         starts = np.tile(np.asarray(start, dtype=np.float64).reshape(1, -1), (nchains, 1))
     starts = starts.reshape(nchains, d)
-
-    if seed is None:
-        seed = int.from_bytes(os.urandom(8), 'little')
 
     import time
     timing = os.environ.get('DREAMZS_TIMING')
@@ -194,6 +210,24 @@ def run_dream(parameters, likelihood, nchains=5, niterations=50000, start=None, 
         print('run_dream stages (ms): engine+upload %.2f, enqueue %.2f, drain %.2f, lists %.2f'
               % (1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (t_d - t_c), 1e3 * (time.perf_counter() - t_d)))
     return sampled_params, log_ps
+
+
+def _world_size(group):
+    import torch.distributed as dist
+    return dist.get_world_size(group)
+
+
+def _rank(group):
+    import torch.distributed as dist
+    return dist.get_rank(group)
+
+
+def _broadcast_from_rank0(obj, group):
+    """The object rank 0 of `group` holds, on every rank (host-side inputs of a sharded run_dream)."""
+    import torch.distributed as dist
+    box = [obj]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0), group=group)
+    return box[0]
 
 
 def _print_tempering(dec, swaps, niterations, nchains):

@@ -12,8 +12,10 @@ Data layout in HBM (all float64, row stride ``ld`` = ndim rounded up to 4 double
     trace  [N_local, T, ld]      sampled_params (chain-major: chain c's trace is contiguous)
     logp   [N_local, T]          log_ps
     dec    [N_local, T] uint32   decision words (accept / snooker / CR / gamma level / multi-try pick)
-Sharding: rank r owns global chains [r*N/G, (r+1)*N/G); Z is replicated; after every appending
-launch the new rows are all-gathered in place over NCCL (NVLink/NVSwitch) straight into Z's tail.
+Sharding: rank r owns global chains [r*N/G, (r+1)*N/G); Z is replicated on every GPU.  The appending iteration of
+a launch stores each new row into ALL replicas (peer stores over NVLink from inside the step kernel, system-scope
+flags; `dreamzs_peers`); when the ranks cannot map each other's memory the rows are all-gathered in place with
+NCCL after every appending launch instead.
 """
 import ctypes as C
 import math
@@ -216,6 +218,10 @@ class DreamEngine:
         if self.Z is not None and self.Z.shape[0] >= rows:
             return
         old = self.Z
+        if old is not None:
+            # geometric growth: an astep() / run() loop that appends a few rows per call must not re-allocate and copy the
+            # whole archive every time (and, sharded, pay a barrier + IPC re-mapping every time)
+            rows = max(int(rows), old.shape[0] + old.shape[0] // 2 + self.N)
         if self._want_peers:
             Z = self._alloc_shared(rows)
         else:
@@ -237,6 +243,12 @@ class DreamEngine:
         self.Z = Z
         if self.peers is not None:
             self._finish_shared()
+        if getattr(self, '_shared_stale', None) is not None:      # fell back to NCCL while growing: drop the old mappings
+            torch.cuda.synchronize(self.device)
+            torch.distributed.barrier(self.group)
+            self._shared, stale = self._shared_stale, None
+            self._shared_stale = None
+            self._release_shared()
         if hasattr(self, 'st'):
             self._state()
 
@@ -274,6 +286,11 @@ class DreamEngine:
             if base.value:
                 lib.dreamzs_shared_free(base)
             self._want_peers = False
+            # from here on every rank keeps a private archive and the NCCL all-gather carries the appended rows; an
+            # earlier shared block (the archive was growing) is released once _ensure_capacity has copied it
+            self.peers = None
+            self._shared_stale = self._shared
+            self._shared = None
             return torch.empty((rows, self.ld), dtype=torch.float64, device=self.device)
         block = torch.as_tensor(_DevicePtr(base.value, nbytes), device=self.device)
         if self._shared is not None:                  # growing: the flags published so far carry over
@@ -316,6 +333,23 @@ class DreamEngine:
             self.Z = None
             self.peers = None
             self._release_shared()
+
+    def rewind(self):
+        """Collective.  Forget the rows appended so far (the archive is back to its seed rows) and restart the iteration
+        counter at 0; the chains keep their positions.  The next run re-uses the same archive rows, so a benchmark can
+        repeat a run of any length inside a fixed amount of memory."""
+        torch.cuda.synchronize(self.device)
+        if self.group is not None:
+            torch.distributed.barrier(self.group)     # no peer is still storing rows / flags into this replica
+        self.count, self.iter = 0, 0
+        if self._shared is not None:
+            self._shared['block'][:SHARED_HEADER].zero_()       # append flags, error word, appended-chains counter
+            torch.cuda.synchronize(self.device)
+            torch.distributed.barrier(self.group)
+        if not self.external:
+            # first-call branch again: last_prior / last_like (and the window kernel's carried state) from X
+            _cabi.check(self.lib.dreamzs_init_logp(C.byref(self.cfg), C.byref(self.st), self._stream()), 'dreamzs_init_logp')
+            self.launches += 1
 
     def check_peers(self):
         """Raise if a wait for a peer's append timed out (DREAMZS_PEER_TIMEOUT_NS), or if a multi-try batch of the split

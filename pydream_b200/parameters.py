@@ -17,9 +17,12 @@ class SampledParam():
     def interval(self, alpha=1):
         return self.dist.interval(alpha)
 
-    def random(self, reseed=False):
-        random_seed = np.random.RandomState() if reseed else None
-        return self.dist.rvs(random_state=random_seed)
+    def random(self, reseed=False, random_state=None):
+        """One draw (pydream/parameters.py:27-35).  `random_state` (extension): a numpy Generator / RandomState to draw
+        from, which is how run_dream(seed=...) makes its prior draws reproducible."""
+        if random_state is None:
+            random_state = np.random.RandomState() if reseed else None
+        return self.dist.rvs(random_state=random_state)
 
     def prior(self, q0):
         return np.sum(self.dist.logpdf(q0))

@@ -176,3 +176,28 @@ class TorchLikelihood(AnalyticTarget):
         import torch
         x = torch.as_tensor(np.asarray(param_vec, dtype=np.float64).reshape(1, -1), device='cuda')
         return float(self.evaluate(x)[0].item())
+
+
+class HostLikelihood(TorchLikelihood):
+    """The reference's own likelihood contract, ``likelihood(param_vec: np.ndarray[ndim]) -> float`` (pydream/model.py:30):
+    an arbitrary Python callable evaluated on the HOST, one point at a time (or by ``pool.map`` when a pool is given, the
+    counterpart of Dream's ``parallel=True``).  The MT-DREAM(ZS) step itself stays on the GPU (dreamzs_propose /
+    dreamzs_select / dreamzs_accept); only the proposals travel to the host and their log-likelihoods back, as the
+    reference hands them to the user's function.  run_dream wraps plain callables in this class."""
+
+    def __init__(self, ndim, fn, pool=None):
+        super().__init__(ndim, fn)
+        self.pool = pool
+
+    def evaluate(self, points):
+        import torch
+        pts = points.detach().cpu().numpy()
+        if self.pool is not None:
+            vals = self.pool.map(self.fn, [p for p in pts])
+        else:
+            vals = [self.fn(p) for p in pts]
+        out = np.asarray([float(v) for v in vals], dtype=np.float64)
+        return torch.from_numpy(out).to(points.device)
+
+    def __call__(self, param_vec):
+        return float(self.fn(np.asarray(param_vec, dtype=np.float64)))

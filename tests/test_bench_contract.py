@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _run(env_extra):
     env = dict(os.environ, **env_extra)
-    return subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '1', '--steps', '30',
-                           '--warmup', '3'], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    return subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '1', '--steps', '6',
+                           '--warmup', '3', '--cpu-budget', '5'], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
 
 
 def test_reference_arm_line():
@@ -26,6 +26,8 @@ def test_reference_arm_line():
         assert key in j, key
     assert j['value'] > 0 and j['higher_is_better'] is True and j['vs_baseline'] is None and j['dtype'] == 'f64'
     assert 'workload' in j['config'] and j['config']['ndim'] == 100 and j['config']['nchains'] == 1024
+    assert j['steps'] == 6 and j['warmup'] == 3 and j['config']['iters_per_step'] == 1000      # the main arm's step definition
+    assert 5 <= j['sampled_iterations_per_step'] <= 1000
     cb = j['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == j['value'] and cb['sample']
     assert j['e2e'] == dict(value=j['value'], unit=j['unit'], h2d_bytes_per_step=0, d2h_bytes_per_step=0)

@@ -1,6 +1,7 @@
 """Split step for caller-evaluated likelihoods (dreamzs_propose -> torch callable -> dreamzs_accept; SURVEY.md 8(f)
-row 2): with a torch restatement of an analytic target it must reproduce the fused in-kernel step -- identical
-decisions and draws, log-posteriors within 1e-12 * max(1, |logp|)."""
+row 2): with a torch restatement of an analytic target it must reproduce the C oracle (the checker pinned to the
+unmodified reference) and the fused in-kernel step -- identical decisions and draws, log-posteriors within
+1e-12 * max(1, |logp|)."""
 import numpy as np
 import pytest
 from scipy.stats import uniform
@@ -16,6 +17,33 @@ def _run(eng, T):
     d = eng.d
     return (trace[:, :, :d].permute(1, 0, 2).contiguous().cpu().numpy(), logp.t().contiguous().cpu().numpy(),
             dec.t().contiguous().cpu().numpy().astype(np.uint32))
+
+
+def _oracle(d, N, hist, tgt, T, kw):
+    """The same run on the C oracle -> (states, logp, decisions), iteration-major like _run."""
+    from oracle import c_oracle
+    kw = dict(kw)
+    seed = kw.pop('seed')
+    ref = c_oracle.OracleSampler(d, N, hist, hist[:N].copy(), tgt.kind, tgt.table(), seed=seed, nthreads=4, **kw).run(T)
+    return ref['states'], ref['logp'], ref['decisions']
+
+
+def _assert_matches_oracle(got, ref):
+    np.testing.assert_array_equal(got[2], ref[2])
+    assert np.all(np.abs(got[1] - ref[1]) <= logp_tol(ref[1])), (np.abs(got[1] - ref[1]) / logp_tol(ref[1])).max()
+    np.testing.assert_allclose(got[0], ref[0], rtol=1e-10, atol=1e-11)
+
+
+def _oracle_run_dream(lower, upper, hist, nchains, niter, seed, **kw):
+    """What run_dream does with its defaults (crossover adaptation during the first niter/10 iterations) on the oracle:
+    SumShift target, uniform prior on [lower, upper]."""
+    from oracle import c_oracle
+    tgt = targets.SumShift(len(lower), 3.0)
+    pk = np.full(len(lower), 2, dtype=np.int32)
+    orc = c_oracle.OracleSampler(len(lower), nchains, hist, hist[:nchains].copy(), tgt.kind, tgt.table(), seed=seed,
+                                 prior_kind=pk, prior_a=lower, prior_b=upper - lower, adapt_crossover=True,
+                                 crossover_burnin=niter // 10, **kw)
+    return orc.run(niter)
 
 
 def _torch_mixture(tgt):
@@ -46,6 +74,7 @@ def test_external_mixture_equals_fused(adapt):
     b = _run(eng, 17)
     b2 = _run(eng, T - 17)          # a second call continues the same chains
     b = tuple(np.concatenate([b[i], b2[i]], axis=0) for i in range(3))
+    _assert_matches_oracle(b, _oracle(d, N, hist, tgt, T, kw))      # the split step against the checker itself
     np.testing.assert_array_equal(a[2], b[2])
     assert np.all(np.abs(a[1] - b[1]) <= logp_tol(a[1])), (np.abs(a[1] - b[1]) / logp_tol(a[1])).max()
     np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=1e-13)
@@ -65,7 +94,10 @@ def test_external_with_bounded_prior_and_run_dream():
     ref_s, ref_l = run_dream(params, targets.SumShift(4, 3.0), **kw)
     ext = targets.TorchLikelihood(4, lambda x: (x + 3.0).sum(dim=1))
     s, l = run_dream(params, ext, **kw)
+    orc = _oracle_run_dream(lower, upper, hist, 6, 200, 9)
     for c in range(6):
+        np.testing.assert_allclose(s[c], orc['states'][:, c, :], rtol=1e-10, atol=1e-11)
+        assert np.all(np.abs(l[c][:, 0] - orc['logp'][:, c]) <= logp_tol(orc['logp'][:, c]))
         np.testing.assert_allclose(s[c], ref_s[c], rtol=1e-12)
         np.testing.assert_allclose(l[c], ref_l[c], rtol=1e-12)
         assert np.all(s[c] >= lower) and np.all(s[c] <= upper)
@@ -86,6 +118,7 @@ def test_external_multitry_equals_fused(k, snooker):
     eng = DreamEngine(d, N, hist, hist[:N], targets.TorchLikelihood(d, _torch_mixture(tgt)), **kw)
     b = _run(eng, T)
     eng.check_peers()
+    _assert_matches_oracle(b, _oracle(d, N, hist, tgt, T, kw))      # the split step against the checker itself
     np.testing.assert_array_equal(a[2], b[2])
     assert np.all(np.abs(a[1] - b[1]) <= logp_tol(a[1])), (np.abs(a[1] - b[1]) / logp_tol(a[1])).max()
     np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=1e-13)
@@ -104,6 +137,9 @@ def test_external_multitry_bounded_prior():
               verbose=False, save_history=False, seed=10, multitry=3)
     ref_s, ref_l = run_dream(params, targets.SumShift(4, 3.0), **kw)
     s, l = run_dream(params, targets.TorchLikelihood(4, lambda x: (x + 3.0).sum(dim=1)), **kw)
+    orc = _oracle_run_dream(lower, upper, hist, 7, 150, 10, multitry=3)
     for c in range(7):
+        np.testing.assert_allclose(s[c], orc['states'][:, c, :], rtol=1e-10, atol=1e-11)
+        assert np.all(np.abs(l[c][:, 0] - orc['logp'][:, c]) <= logp_tol(orc['logp'][:, c]))
         np.testing.assert_allclose(s[c], ref_s[c], rtol=1e-12)
         np.testing.assert_allclose(l[c], ref_l[c], rtol=1e-12)

@@ -1,6 +1,9 @@
-"""Size-independent properties at BASELINE.json's full single-GPU sizes (the oracle is too slow there):
-the archive tail is exactly the states at the appending iterations, rejected steps repeat the previous state,
-the log-posterior trace is the target evaluated on the trace, and two independent kernels agree."""
+"""BASELINE.json's full single-GPU sizes: (a) the CUDA path against the C oracle on the same seeded inputs
+(decision words bit-exact, log-posteriors within the north_star tolerance, states rtol 1e-10) -- C2 1024 x 100,
+C3 4096 x 10 multi-try 5, C4's per-GPU share 4096 x 200, C5-shaped 8192 x 50 with crossover adaptation; the oracle
+runs on the host threads and takes seconds at these sizes -- and (b) size-independent properties: the archive tail
+is exactly the states at the appending iterations, rejected steps repeat the previous state, the log-posterior
+trace is the target evaluated on the trace, and two independent kernels agree."""
 import numpy as np
 import pytest
 
@@ -8,6 +11,68 @@ from golden_util import logp_tol, decode_decisions
 from pydream_b200 import targets
 
 pytestmark = pytest.mark.gpu
+
+
+def _oracle_parity(d, N, T, tgt, hist, kw, seed):
+    """The same run through the CUDA path (C ABI) and the C oracle; returns the oracle's result dict."""
+    import os
+    from oracle import c_oracle
+    from pydream_b200.engine import DreamEngine
+    starts = hist[:N].copy()
+    nthreads = max(1, min(32, len(os.sched_getaffinity(0))))
+    orc = c_oracle.OracleSampler(d, N, hist, starts, tgt.kind, tgt.table(), seed=seed, nthreads=nthreads, **kw)
+    ref = orc.run(T)
+    eng = DreamEngine(d, N, hist, starts, tgt, seed=seed, **kw)
+    trace, logp, dec = eng.run(T)
+    got_dec = dec.t().contiguous().cpu().numpy().astype(np.uint32)
+    got_logp = logp.t().contiguous().cpu().numpy()
+    got_states = trace[:, :, :d].permute(1, 0, 2).contiguous().cpu().numpy()
+    np.testing.assert_array_equal(got_dec, ref['decisions'])                     # accept / reject, snooker, CR, gamma level, pick
+    err = np.abs(got_logp - ref['logp'])
+    assert np.all(err <= logp_tol(ref['logp'])), (err / logp_tol(ref['logp'])).max()
+    np.testing.assert_allclose(got_states, ref['states'], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(eng.history_flat(), orc.history_flat, rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(eng.cr_probs.cpu().numpy(), orc.cr_probs, rtol=1e-10)
+    return ref
+
+
+def test_c2_full_size_matches_oracle():
+    """BASELINE config 2: 100-D correlated Gaussian, 1024 chains, snooker .1, thin 10, 200 iterations (20 windows of
+    the window kernel, 5 refreshes of the carried state), archive seed 2N rows."""
+    d, N, T = 100, 1024, 200
+    rng = np.random.default_rng(142)
+    tgt = targets.CorrelatedGaussian.benchmark(d)
+    hist = rng.uniform(-5, 15, size=(2 * N, d))
+    ref = _oracle_parity(d, N, T, tgt, hist, dict(snooker=.1, history_thin=10), seed=21)
+    assert 0.02 < (ref['decisions'] & 1).mean() < 0.9
+
+
+def test_c3_full_size_matches_oracle():
+    """BASELINE config 3: 10-D bimodal mixture, 4096 chains, multi-try 5 + snooker, 40 iterations."""
+    d, N, T = 10, 4096, 40
+    rng = np.random.default_rng(143)
+    tgt = targets.BimodalMixture.benchmark(d)
+    hist = rng.normal(size=(2 * N, d))
+    _oracle_parity(d, N, T, tgt, hist, dict(snooker=.1, history_thin=10, multitry=5), seed=22)
+
+
+def test_c4_share_matches_oracle():
+    """BASELINE config 4, the per-GPU share at 2 GPUs: 200-D twisted Gaussian, 4096 chains, 30 iterations."""
+    d, N, T = 200, 4096, 30
+    rng = np.random.default_rng(144)
+    tgt = targets.Banana(d, 0.1)
+    hist = rng.normal(size=(2 * N, d)) * np.sqrt(np.concatenate([[100.0], np.ones(d - 1)]))
+    _oracle_parity(d, N, T, tgt, hist, dict(snooker=.1, history_thin=10), seed=23)
+
+
+def test_c5_shape_matches_oracle():
+    """BASELINE config 5's shape at 8192 chains: 50-D correlated Gaussian, crossover adaptation during a 30-iteration
+    burn-in (the adapted probabilities are compared as well), 60 iterations."""
+    d, N, T = 50, 8192, 60
+    rng = np.random.default_rng(145)
+    tgt = targets.CorrelatedGaussian.benchmark(d)
+    hist = rng.uniform(-5, 15, size=(2 * N, d))
+    _oracle_parity(d, N, T, tgt, hist, dict(snooker=.1, history_thin=10, adapt_crossover=True, crossover_burnin=30), seed=24)
 
 
 def _check_invariants(eng, trace, logp, dec, tgt, nseed, thin, starts):

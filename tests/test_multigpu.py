@@ -77,3 +77,42 @@ def test_sharded_equals_single_gpu(name, peer_archive, tmp_path):
         assert torch.equal(p['Z'], eng.Z[:eng.archive_rows].cpu())
         np.testing.assert_allclose(p['cr'].numpy(), eng.cr_probs.cpu().numpy(), rtol=1e-12)
         np.testing.assert_allclose(p['rhat'].numpy(), rhat.numpy(), rtol=1e-12)
+
+
+def _worker_run_dream(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from scipy.stats import norm
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from pydream_b200 import targets
+    from pydream_b200.core import run_dream
+    from pydream_b200.parameters import SampledParam
+    params = [SampledParam(norm, loc=np.array([-6.6, 3, 1.0, -.12]), scale=np.array([.13, 5, .9, 1.0]))]
+    s, l = run_dream(params, targets.SumShift(4, 3.0), niterations=50, nchains=8, verbose=False, save_history=False,
+                     seed=1234, group=dist.group.WORLD)
+    np.savez(out % rank, s=np.stack(s), l=np.stack(l))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_run_dream_draws_on_rank0(tmp_path):
+    """run_dream(group=...) WITHOUT history_file / start: the archive seed, the random starts (prior draws on the host) and
+    the seed are drawn on rank 0 and broadcast, so the sharded run equals the single-GPU run with the same seed."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from scipy.stats import norm
+    from pydream_b200 import targets
+    from pydream_b200.core import run_dream
+    from pydream_b200.parameters import SampledParam
+    params = [SampledParam(norm, loc=np.array([-6.6, 3, 1.0, -.12]), scale=np.array([.13, 5, .9, 1.0]))]
+    s1, l1 = run_dream(params, targets.SumShift(4, 3.0), niterations=50, nchains=8, verbose=False, save_history=False, seed=1234)
+    out = str(tmp_path / 'rd%d.npz')
+    mp.spawn(_worker_run_dream, args=(2, 29700 + os.getpid() % 1000, out), nprocs=2, join=True)
+    parts = [np.load(out % r) for r in range(2)]
+    np.testing.assert_array_equal(np.concatenate([p['s'] for p in parts]), np.stack(s1))
+    np.testing.assert_array_equal(np.concatenate([p['l'] for p in parts]), np.stack(l1))

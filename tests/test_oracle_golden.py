@@ -191,3 +191,21 @@ def test_gamma_table_known_answers():
             ref[lvl - 1, delta - 1, :] = (2.38 / np.sqrt(2 * delta * np.linspace(1, 7, num=7))) / dec
         dec *= 2
     np.testing.assert_array_equal(tab, ref)
+
+
+def test_gelman_rubin_matches_reference_function():
+    """`Gelman_Rubin` has no test in the reference: the C restatement against the imported
+    pydream.convergence.Gelman_Rubin (pydream/convergence.py:3-20) on random chains, odd and even lengths."""
+    from oracle import ref_harness as H
+    if not H.reference_available():
+        pytest.skip('reference not present (neither /root/reference nor baseline/_ref)')
+    import sys
+    if H.REF_ROOT not in sys.path:
+        sys.path.insert(0, H.REF_ROOT)
+    from pydream.convergence import Gelman_Rubin
+    rng = np.random.default_rng(11)
+    for nchains, nsamples, d in ((3, 40, 1), (5, 501, 7), (8, 1000, 10), (16, 63, 4)):
+        chains = [rng.normal(size=(nsamples, d)) * (1 + .2 * c) + .1 * c for c in range(nchains)]
+        ref = Gelman_Rubin(chains)
+        got = c_oracle.gelman_rubin(np.stack(chains))
+        np.testing.assert_allclose(got, ref, rtol=1e-12)

@@ -19,7 +19,7 @@ from golden_util import make_target, prior_arrays, sampler_kwargs, logp_tol  # n
 from oracle import c_oracle                                                  # noqa: E402
 
 
-def check(meta, hist):
+def check(meta, hist, lp_factor=10, rtol=1e-9):
     from pydream_b200.engine import DreamEngine
     d, N, T = meta['target']['d'], meta['N'], meta['T']
     starts = hist[:N].copy()
@@ -45,11 +45,11 @@ def check(meta, hist):
         ref_dec, ref_lp, ref_sp = ref['decisions'], ref['logp'], ref['states']
     assert np.array_equal(got_dec, ref_dec), 'decisions differ at %s' % (np.argwhere(got_dec != ref_dec)[:3].tolist(),)
     err = np.abs(got_lp - ref_lp) / logp_tol(ref_lp)
-    assert np.all(err <= 10), 'logp: %.2f x tolerance' % err.max()
-    np.testing.assert_allclose(got_sp, ref_sp, rtol=1e-9, atol=1e-10)
-    np.testing.assert_allclose(eng.history_flat(), orc.history_flat, rtol=1e-9, atol=1e-10)
-    np.testing.assert_allclose(eng.cr_probs.cpu().numpy(), orc.cr_probs, rtol=1e-9)
-    np.testing.assert_allclose(eng.gamma_probs.cpu().numpy(), orc.gamma_probs, rtol=1e-9)
+    assert np.all(err <= lp_factor), 'logp: %.2f x tolerance' % err.max()
+    np.testing.assert_allclose(got_sp, ref_sp, rtol=rtol, atol=rtol / 10)
+    np.testing.assert_allclose(eng.history_flat(), orc.history_flat, rtol=rtol, atol=rtol / 10)
+    np.testing.assert_allclose(eng.cr_probs.cpu().numpy(), orc.cr_probs, rtol=rtol)
+    np.testing.assert_allclose(eng.gamma_probs.cpu().numpy(), orc.gamma_probs, rtol=rtol)
 
 
 def main():
