@@ -64,20 +64,62 @@ static void stream_uniform32_vec(stream_t *s, int st, int n, double *out) {
     for (int j = 0; j < 4 && 4 * b + j < n; ++j) out[4 * b + j] = (double)w[j] * (1.0 / 4294967296.0);
   }
 }
-/* Box-Muller on word pairs, see oracle/philox.py Stream.normal_vec */
+/* Normal variates of the contract (stream 2): Box-Muller in float32 on 24-bit uniforms, written with operations
+ * that round identically everywhere (float add / multiply / fmaf / sqrtf on fixed Cephes coefficients); the recipe
+ * is documented in oracle/philox.py (normal_pairs32).  Compiled with -ffp-contract=off: only the explicit fmaf()
+ * calls fuse. */
+static void normal_pair32(uint32_t w0, uint32_t w1, float *n0, float *n1) {
+  static const float LOG_P[9] = {7.0376836292E-2f, -1.1514610310E-1f, 1.1676998740E-1f, -1.2420140846E-1f, 1.4249322787E-1f,
+                                 -1.6668057665E-1f, 2.0000714765E-1f, -2.4999993993E-1f, 3.3333331174E-1f};
+  const float a = (float)((w0 >> 8) + 1u);
+  uint32_t bits; memcpy(&bits, &a, 4);
+  int E = (int)(bits >> 23) - 127;
+  uint32_t mb = (bits & 0x007FFFFFu) | 0x3F800000u;
+  float m; memcpy(&m, &mb, 4);
+  if (m > 1.41421356f) { m = m * 0.5f; E += 1; }
+  const float t = m - 1.0f, z = t * t;
+  float P = LOG_P[0];
+  for (int i = 1; i < 9; ++i) P = fmaf(P, t, LOG_P[i]);
+  float y = t * (z * P);
+  y = fmaf(-0.5f, z, y);
+  const float logm = t + y;
+  const float L = fmaf((float)(E - 24), 0.6931471805599453f, logm);
+  const float val = -2.0f * L;
+  const float r = sqrtf(val > 0.0f ? val : 0.0f);
+  const int32_t w24 = (int32_t)(w1 >> 8);
+  const int32_t k = (w24 + (1 << 21)) >> 22;
+  const float g = (float)(w24 - (k << 22)) * 5.9604644775390625e-08f;   /* 2^-24, exact */
+  const float phi = g * 6.283185307179586f;
+  const float zz = phi * phi;
+  const float sp = fmaf(fmaf(-1.9515295891E-4f, zz, 8.3321608736E-3f), zz, -1.6666654611E-1f);
+  const float cp = fmaf(fmaf(2.443315711809948E-5f, zz, -1.388731625493765E-3f), zz, 4.166664568298827E-2f);
+  const float s = fmaf(phi * zz, sp, phi);
+  const float c = fmaf(zz * zz, cp, fmaf(-0.5f, zz, 1.0f));
+  const int q = k & 3;
+  const float cs = q == 0 ? c : q == 1 ? -s : q == 2 ? -c : s;
+  const float sn = q == 0 ? s : q == 1 ? c : q == 2 ? -s : -c;
+  *n0 = r * cs; *n1 = r * sn;
+}
 static void stream_normal_vec(stream_t *s, int n, double *out) {
   uint32_t c1 = stream_next(s, ST_NORMAL), w[4];
-  const double two_pi = 2.0 * 3.141592653589793;
   for (int b = 0; 4 * b < n; ++b) {
     stream_block(s, c1, (uint32_t)b, w);
     for (int h = 0; h < 2; ++h) {
-      double r = sqrt(-2.0 * log(((double)w[2 * h] + 1.0) * (1.0 / 4294967296.0)));
-      double t = two_pi * ((double)w[2 * h + 1] * (1.0 / 4294967296.0));
+      float n0, n1;
+      normal_pair32(w[2 * h], w[2 * h + 1], &n0, &n1);
       int i = 4 * b + 2 * h;
-      if (i < n) out[i] = r * cos(t);
-      if (i + 1 < n) out[i + 1] = r * sin(t);
+      if (i < n) out[i] = (double)n0;
+      if (i + 1 < n) out[i + 1] = (double)n1;
     }
   }
+}
+/* test hook: the float32 normals of word pairs (tests/test_philox.py pins the three implementations to each other) */
+void dreamzs_oracle_normal_pairs32(const uint32_t *w0, const uint32_t *w1, int64_t n, float *n0, float *n1) {
+  for (int64_t i = 0; i < n; ++i) normal_pair32(w0[i], w1[i], n0 + i, n1 + i);
+}
+/* test hook: fmaf, to check the numpy emulation in oracle/philox.py */
+void dreamzs_oracle_fmaf(const float *a, const float *b, const float *c, int64_t n, float *out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = fmaf(a[i], b[i], c[i]);
 }
 /* random.sample(range(M), n) restated on the counter stream (pydream/Dream.py:662-664) */
 static void stream_sample(stream_t *s, int64_t M, int n, int64_t *rows) {

@@ -80,6 +80,85 @@ def u53(w0, w1):
     return ((int(w0) >> 5) * 67108864 + (int(w1) >> 6)) * TWO_M53
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Normal variates of the contract (stream 2).  zeta of Dream.py:694 is N(0, 1e-12): a jitter ~12 orders of magnitude
+# below the states it is added to, so float32 resolution is ample; what the contract needs is that every
+# implementation (this file, oracle/dreamzs_oracle.c, the CUDA kernels) produces THE SAME BITS.  The recipe below
+# therefore uses only operations that IEEE-754 rounds identically everywhere -- float32 add, multiply, fused
+# multiply-add and square root, round to nearest even -- on fixed polynomial coefficients (Cephes logf / sinf / cosf):
+#
+#   pair(w0, w1):  a = (w0 >> 8) + 1                      in [1, 2^24]        (u = a 2^-24 in (0, 1])
+#                  a = m 2^E, m in [1, 2);  m > 1.41421356f: m <- m/2, E <- E+1;  t = m - 1
+#                  log m = t + (t (t^2 P(t)) - 0.5 t^2),  P = Horner of LOG_P with fma
+#                  L = fma(E - 24, ln 2, log m);  r = sqrt(max(-2 L, 0))
+#                  v = (w1 >> 8) 2^-24 in [0, 1):  k = round(4 v) (0..4), g = v - k/4 in [-1/8, 1/8), phi = g * 2 pi
+#                  z = phi^2;  s = fma(phi z, SIN_P(z), phi);  c = fma(z z, COS_P(z), fma(-0.5, z, 1))
+#                  (cos, sin)(2 pi v) = quadrant rotation k & 3 of (c, s):  (c, s), (-s, c), (-c, -s), (s, -c)
+#                  pair = (r * cos, r * sin)
+# numpy has no fused multiply-add: `fma32` evaluates a*b exactly in float64, adds c with round-to-odd (TwoSum error
+# term) and rounds once to float32, which equals the IEEE float32 fma for all inputs used here.
+F32 = np.float32
+LOG_P = [F32(x) for x in (7.0376836292E-2, -1.1514610310E-1, 1.1676998740E-1, -1.2420140846E-1, 1.4249322787E-1,
+                          -1.6668057665E-1, 2.0000714765E-1, -2.4999993993E-1, 3.3333331174E-1)]
+SIN_P = [F32(x) for x in (-1.9515295891E-4, 8.3321608736E-3, -1.6666654611E-1)]
+COS_P = [F32(x) for x in (2.443315711809948E-5, -1.388731625493765E-3, 4.166664568298827E-2)]
+LN2_F = F32(0.6931471805599453)
+SQRT2_F = F32(1.41421356)
+TWO_PI_F = F32(6.283185307179586)
+
+
+def fma32(a, b, c):
+    """IEEE float32 fused multiply-add on numpy arrays (exact product in float64, round-to-odd sum, one rounding)."""
+    a, b, c = (np.asarray(x, dtype=np.float32).astype(np.float64) for x in (a, b, c))
+    p = a * b                                   # exact: 24 + 24 significant bits
+    s = p + c
+    bb = s - p
+    err = (p - (s - bb)) + (c - bb)             # TwoSum: p + c == s + err exactly
+    si = np.atleast_1d(s).view(np.int64).copy()
+    up = (np.atleast_1d(err) > 0) == (np.atleast_1d(s) > 0)          # the exact sum is larger in magnitude than s
+    fix = (np.atleast_1d(err) != 0) & ((si & 1) == 0)
+    si = np.where(fix, si + np.where(up, 1, -1), si)
+    return si.view(np.float64).reshape(np.shape(s)).astype(np.float32)
+
+
+def _horner32(coefs, x):
+    acc = np.full(np.shape(x), coefs[0], dtype=np.float32)
+    for c in coefs[1:]:
+        acc = fma32(acc, x, c)
+    return acc
+
+
+def normal_pairs32(w0, w1):
+    """Two standard normals (float32) per pair of 32-bit words; see the recipe above."""
+    w0 = np.asarray(w0, dtype=np.uint32)
+    w1 = np.asarray(w1, dtype=np.uint32)
+    a = ((w0 >> np.uint32(8)) + np.uint32(1)).astype(np.float32)            # exact
+    bits = a.view(np.uint32)
+    E = (bits >> np.uint32(23)).astype(np.int32) - 127
+    m = ((bits & np.uint32(0x007FFFFF)) | np.uint32(0x3F800000)).view(np.float32)
+    big = m > SQRT2_F
+    m = np.where(big, m * F32(0.5), m).astype(np.float32)
+    E = E + big.astype(np.int32)
+    t = (m - F32(1.0)).astype(np.float32)
+    z = (t * t).astype(np.float32)
+    y = (t * (z * _horner32(LOG_P, t)).astype(np.float32)).astype(np.float32)
+    y = fma32(F32(-0.5), z, y)
+    logm = (t + y).astype(np.float32)
+    L = fma32((E - 24).astype(np.float32), LN2_F, logm)
+    r = np.sqrt(np.maximum((F32(-2.0) * L).astype(np.float32), F32(0.0))).astype(np.float32)
+    w24 = (w1 >> np.uint32(8)).astype(np.int64)
+    k = (w24 + (1 << 21)) >> 22
+    g = ((w24 - (k << 22)).astype(np.float32) * F32(2.0 ** -24)).astype(np.float32)   # exact
+    phi = (g * TWO_PI_F).astype(np.float32)
+    zz = (phi * phi).astype(np.float32)
+    s = fma32((phi * zz).astype(np.float32), _horner32(SIN_P, zz), phi)
+    c = fma32((zz * zz).astype(np.float32), _horner32(COS_P, zz), fma32(F32(-0.5), zz, F32(1.0)))
+    q = k & 3
+    cs = np.where(q == 0, c, np.where(q == 1, -s, np.where(q == 2, -c, s))).astype(np.float32)
+    sn = np.where(q == 0, s, np.where(q == 1, c, np.where(q == 2, -s, -c))).astype(np.float32)
+    return (r * cs).astype(np.float32), (r * sn).astype(np.float32)
+
+
 class Stream:
     """Per-(seed, chain, iteration) view of the counter space with running call numbers."""
 
@@ -111,14 +190,12 @@ class Stream:
         return self.words(stream, n).astype(np.float64) * TWO_M32
 
     def normal_vec(self, n):
-        """Box-Muller on 32-bit words: block b=(w0,w1,w2,w3) -> elements 4b..4b+3 =
-        r(w0)cos(t(w1)), r(w0)sin(t(w1)), r(w2)cos(t(w3)), r(w2)sin(t(w3)),
-        r(w)=sqrt(-2 ln((w+1)2^-32)), t(w)=2 pi w 2^-32."""
+        """Box-Muller in float32 on 24-bit uniforms (`normal_pairs32`): block b=(w0,w1,w2,w3) -> elements 4b..4b+3 =
+        pair(w0,w1), pair(w2,w3); returned as float64 (exact widening)."""
         nb = (n + 3) // 4
-        w = self.words(ST_NORMAL, 4 * nb).astype(np.float64).reshape(nb, 2, 2)
-        r = np.sqrt(-2.0 * np.log((w[:, :, 0] + 1.0) * TWO_M32))
-        t = (2.0 * np.pi) * (w[:, :, 1] * TWO_M32)
-        out = np.stack([r * np.cos(t), r * np.sin(t)], axis=2).reshape(-1)
+        w = self.words(ST_NORMAL, 4 * nb).astype(np.uint32).reshape(nb, 2, 2)
+        n0, n1 = normal_pairs32(w[:, :, 0], w[:, :, 1])
+        out = np.stack([n0, n1], axis=2).reshape(-1).astype(np.float64)
         return out[:n]
 
     def sample(self, M, n):
