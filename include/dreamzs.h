@@ -12,7 +12,8 @@
  *
  * Conventions
  *   - all pointers marked "device" are CUDA device pointers owned by the caller; the
- *     library never allocates, frees or keeps them; there is no global state.
+ *     library never allocates, frees or keeps them; there is no global state (except the
+ *     profiling aid dreamzs_debug_set_phase_buffer).
  *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), does
  *     not synchronise the host, and returns 0 on success or a negative DREAMZS_E_* code.
  *   - all floating-point state is float64; chain ids are GLOBAL ids (shard-independent
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DREAMZS_ABI_VERSION 2
+#define DREAMZS_ABI_VERSION 3
 
 /* status codes */
 #define DREAMZS_OK 0
@@ -116,6 +117,21 @@ typedef struct dreamzs_state {
    * DREAMZS_GAUSS_REFRESH_WINDOWS windows of history_thin iterations. */
   double *gauss_Y;
   double *gauss_Q;
+  /* Optional (may be NULL): whitened form of the dense Gaussian, used by the whitened window kernel (flat priors, one
+   * DE pair, no multi-try, ld <= 128) in preference to gauss_Y / gauss_Q.  invC = L L^T (L lower triangular);
+   * gauss_L is L packed for the fp64 MMA path: for i-tile I = 0 .. ceil(ld/8)-1 and k = 2I .. ld/4-1 one tile of 32
+   * doubles, entry (j % 4) + 4 (i % 8) = L[4k + j%4][8I + i%8] (zero outside the matrix), tiles in (I, k) order
+   * (dreamzs_whiten_doubles(ld) doubles, 16-byte aligned).  gauss_U[c] = L^T x_c (nchains_local x ld), maintained by
+   * dreamzs_init_logp / dreamzs_step: Q(x + dx) = |u + L^T dx|^2, re-derived from x every
+   * DREAMZS_GAUSS_REFRESH_WINDOWS windows. */
+  const double *gauss_L;
+  double *gauss_U;
+  /* Optional (may be NULL): scratch words for launches that span several windows (dreamzs_run with the whitened
+   * window kernel): 16 + (windows per launch) uint32.  With it dreamzs_run issues ONE persistent launch for a whole
+   * span of iterations; the CTAs synchronise through these words only where a sampled row was appended inside the
+   * launch.  Without it every window is its own launch. */
+  uint32_t *sync_ws;
+  int64_t sync_ws_words;
 } dreamzs_state;
 
 /* Per-launch outputs (device pointers; any may be NULL except trace/trace_logp). */
@@ -134,6 +150,19 @@ typedef struct dreamzs_trace {
 #define DREAMZS_DECISION_SWAPPED (1u << 20)
 
 int dreamzs_abi_version(void);
+
+/* Length (doubles) of the packed whitening factor dreamzs_state.gauss_L for row stride ld. */
+int64_t dreamzs_whiten_doubles(int32_t ld);
+
+/* RNG contract, normal variates (stream 2; DESIGN.md "RNG contract"): the 4 * nblocks float32 normals of call
+ * `call_no` of chain `chain` at iteration `iter` under `seed`, written to out (device, float32).  Lets a test pin the
+ * kernels' Box-Muller to the oracle's bit for bit. */
+int dreamzs_rng_normals(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t call_no, int32_t nblocks, float *out,
+                        void *stream);
+
+/* Profiling aid, not part of the sampler: CTA 0 of the window kernels writes clock64() stamps of its phases into
+ * `device_ptr` (>= 64 int64; NULL switches it off).  Process-wide; the only global state of the library. */
+void dreamzs_debug_set_phase_buffer(void *device_ptr);
 
 /* Initial log-prior / log-likelihood of the current positions X (first-call branch of
  * astep, Dream.py:266-268 -> Model.total_logp, pydream/model.py:17-32). */

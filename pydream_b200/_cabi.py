@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DREAMZS_LIB') or os.path.join(HERE, 'libdreamzs.so')   # DREAMZS_LIB: A/B testing of builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, E_BADARG, E_LAUNCH, E_UNSUPPORTED = 0, -1, -2, -3
 MAX_NCR, MAX_NGAMMA, MAX_DEPAIRS, MAX_MULTITRY, MAX_NDIM = 16, 8, 8, 16, 1024
 FLAG_ALL_FLAT = 1
@@ -23,7 +23,8 @@ EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_
            'dreamzs_propose', 'dreamzs_select', 'dreamzs_accept', 'dreamzs_step_tempered', 'dreamzs_pt_swap',
            'dreamzs_shared_alloc', 'dreamzs_shared_open', 'dreamzs_shared_close', 'dreamzs_shared_free', 'dreamzs_adapt_workspace_bytes',
            'dreamzs_adapt_colsum', 'dreamzs_adapt_colsq', 'dreamzs_adapt_jumps', 'dreamzs_adapt_finish',
-           'dreamzs_gr_chain_stats', 'dreamzs_gr_finish']
+           'dreamzs_gr_chain_stats', 'dreamzs_gr_finish', 'dreamzs_whiten_doubles', 'dreamzs_rng_normals',
+           'dreamzs_debug_set_phase_buffer']
 
 
 class Config(C.Structure):
@@ -39,7 +40,8 @@ class State(C.Structure):
                 ('last_like', C.c_void_p), ('cr_probs', C.c_void_p), ('gamma_probs', C.c_void_p),
                 ('gamma_table', C.c_void_p), ('target_table', C.c_void_p), ('prior_kind', C.c_void_p),
                 ('prior_a', C.c_void_p), ('prior_b', C.c_void_p), ('mins', C.c_void_p), ('maxs', C.c_void_p),
-                ('gauss_Y', C.c_void_p), ('gauss_Q', C.c_void_p)]
+                ('gauss_Y', C.c_void_p), ('gauss_Q', C.c_void_p), ('gauss_L', C.c_void_p), ('gauss_U', C.c_void_p),
+                ('sync_ws', C.c_void_p), ('sync_ws_words', C.c_int64)]
 
 
 class Trace(C.Structure):
@@ -108,6 +110,9 @@ def load():
         'dreamzs_adapt_finish': (C.c_int, [cfgp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
         'dreamzs_gr_chain_stats': (C.c_int, [vp, i64, i64, i64, i32, i64, vp, vp, vp]),
         'dreamzs_gr_finish': (C.c_int, [vp, vp, i64, i64, i32, vp, vp]),
+        'dreamzs_whiten_doubles': (i64, [i32]),
+        'dreamzs_rng_normals': (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, i32, vp, vp]),
+        'dreamzs_debug_set_phase_buffer': (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

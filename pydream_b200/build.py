@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, 'libdreamzs.so')
 STEP_VARIANTS = [(4, 1), (8, 1), (16, 1), (32, 1), (32, 2), (32, 4), (32, 8)]
 GAUSS_VARIANTS = [7, 8]
 GWIN_VARIANTS = [7, 8]
-PLAIN_UNITS = ['dreamzs_cabi.cu', 'dreamzs_adapt.cu', 'dreamzs_gr.cu', 'dreamzs_pt.cu']
+PLAIN_UNITS = ['dreamzs_cabi.cu', 'dreamzs_adapt.cu', 'dreamzs_gr.cu', 'dreamzs_pt.cu', 'dreamzs_wwin_inst.cu']
 
 # -fmad=false: parity-sensitive element-wise arithmetic must round like numpy;
 # reductions use explicit fma().

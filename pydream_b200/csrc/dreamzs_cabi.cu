@@ -2,6 +2,7 @@
 // dispatch over the <G, R> kernel instantiations (one object file each, dreamzs_step_inst.cu).
 #include <string.h>
 #include "dreamzs_step_params.cuh"
+#include "dreamzs_common.cuh"
 
 using namespace dreamzs;
 
@@ -15,17 +16,22 @@ int dreamzs_launch_gwin_7(dreamzs::StepParams &, cudaStream_t);
 int dreamzs_launch_gwin_8(dreamzs::StepParams &, cudaStream_t);
 int dreamzs_gwin_usable(const dreamzs_config &cfg, int TC);
 int dreamzs_launch_gauss_refresh(const dreamzs::StepParams &, cudaStream_t);
+int dreamzs_wwin_usable(const dreamzs_config &cfg, int sms, int niter);
+int dreamzs_launch_wwin(dreamzs::StepParams &, int sms, cudaStream_t);
+int dreamzs_launch_whiten(const dreamzs::StepParams &, cudaStream_t);
+namespace dreamzs { int wwin_ntiles_host(int ld); }
 
 static long long *g_phase_buffer = nullptr;
-// profiling aid (not part of include/dreamzs.h): CTA 0 of the window kernel writes clock64() stamps of its phases
+// profiling aid (include/dreamzs.h): CTA 0 of the window kernels writes clock64() stamps of its phases
 extern "C" void dreamzs_debug_set_phase_buffer(void *device_ptr) { g_phase_buffer = (long long *)device_ptr; }
 
+// SM count of the CURRENT device (cached per device ordinal: a process may drive several GPUs)
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 148; }
+  int &n = cache[dev & 63];
+  if (n == 0 && (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)) n = 148;
   return n;
 }
 
@@ -56,6 +62,15 @@ static int check_cfg(const dreamzs_config *cfg, const dreamzs_state *st) {
   return DREAMZS_OK;
 }
 
+// dense Gaussian, flat priors, one DE pair, no multi-try, whitening factor given: whitened window kernel
+static bool wwin_eligible(const StepParams &P) {
+  const dreamzs_config &cfg = P.cfg;
+  return cfg.target_kind == DREAMZS_TARGET_GAUSSIAN_DENSE && cfg.multitry == 1 && cfg.nDEpairs == 1 && P.all_flat &&
+         P.st.gauss_L && P.st.gauss_U && !P.temperature && !P.ext_phase && !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL) &&
+         !(cfg.flags & DREAMZS_FLAG_NO_WINDOW_KERNEL) && cfg.ld <= 128 &&
+         dreamzs_wwin_usable(cfg, sm_count(), cfg.history_thin < 16 ? cfg.history_thin : 16);
+}
+
 static bool gwin_eligible(const StepParams &P) {
   const dreamzs_config &cfg = P.cfg;
   const int chunks = cfg.ld / 4;
@@ -70,6 +85,13 @@ static int dispatch(StepParams &P, cudaStream_t stream) {
   P.table_doubles = table_doubles_of(&cfg);
   if (P.table_doubles < 0) return DREAMZS_E_UNSUPPORTED;
   P.nslots = cfg.multitry == 1 ? 1 : (P.ext_phase ? 2 * cfg.multitry - 1 : cfg.multitry + 1);
+  if (wwin_eligible(P)) {
+    if (P.init_only) return DREAMZS_OK;   // handled by the caller (generic evaluation + dreamzs_launch_whiten)
+    P.dbg = g_phase_buffer;
+    const int rc = dreamzs_launch_wwin(P, sm_count(), stream);
+    if (rc != DREAMZS_E_UNSUPPORTED || P.ww_sync) return rc;
+  }
+  if (P.ww_sync) return DREAMZS_E_UNSUPPORTED;   // a multi-window span needs the whitened window kernel
   // dense Gaussian, flat priors, one DE pair, no multi-try, carried y = invC x: window kernel (dreamzs_gwin_kernel.cuh)
   if (gwin_eligible(P)) {
     if (P.init_only) return DREAMZS_OK;   // handled by the caller (generic evaluation + dreamzs_launch_gauss_refresh)
@@ -105,12 +127,40 @@ static int all_flat_hint(const dreamzs_config *cfg) { return cfg->flags & DREAMZ
 
 extern "C" int dreamzs_abi_version(void) { return DREAMZS_ABI_VERSION; }
 
+extern "C" int64_t dreamzs_whiten_doubles(int32_t ld) {
+  if (ld < 4 || (ld & 3)) return 0;
+  return (int64_t)dreamzs::wwin_ntiles_host(ld) * 32;
+}
+
+__global__ void rng_normals_kernel(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t call_no, int nblocks, float *out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  float f[4];
+  normal4f(philox4x32((uint32_t)b, (call_no << 3) | ST_NORMAL, iter, chain, (uint32_t)seed, (uint32_t)(seed >> 32)), f);
+  out[4 * b] = f[0]; out[4 * b + 1] = f[1]; out[4 * b + 2] = f[2]; out[4 * b + 3] = f[3];
+}
+extern "C" int dreamzs_rng_normals(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t call_no, int32_t nblocks, float *out,
+                                   void *stream) {
+  if (nblocks < 0 || !out) return DREAMZS_E_BADARG;
+  if (nblocks == 0) return DREAMZS_OK;
+  rng_normals_kernel<<<(nblocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, chain, iter, call_no, nblocks, out);
+  return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;
+}
+
 extern "C" int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state *st, void *stream) {
   int rc = check_cfg(cfg, st);
   if (rc != DREAMZS_OK) return rc;
   if (cfg->nchains_local == 0) return DREAMZS_OK;
   StepParams P{};
   P.cfg = *cfg; P.st = *st; P.init_only = 1; P.all_flat = all_flat_hint(cfg);
+  if (wwin_eligible(P)) {
+    StepParams G = P;
+    G.st.gauss_L = nullptr; G.st.gauss_Y = nullptr;   // evaluate last_prior / last_like with the generic path ...
+    rc = dispatch(G, (cudaStream_t)stream);
+    if (rc != DREAMZS_OK) return rc;
+    rc = dreamzs_launch_whiten(P, (cudaStream_t)stream);   // ... and derive u = L^T x
+    if (rc != DREAMZS_OK || !(st->gauss_Y && st->gauss_Q)) return rc;
+  }
   if (gwin_eligible(P)) {
     StepParams G = P;
     G.st.gauss_Y = nullptr;   // evaluate last_prior / last_like with the generic path ...
@@ -123,7 +173,7 @@ extern "C" int dreamzs_init_logp(const dreamzs_config *cfg, const dreamzs_state 
 
 static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter_begin,
                      int32_t niter, int64_t archive_rows, const dreamzs_peers *peers, uint64_t wait_k, uint64_t publish_k,
-                     void *stream, const double *temperature = nullptr);
+                     void *stream, const double *temperature = nullptr, bool multi = false, uint64_t k0 = 0);
 
 extern "C" int dreamzs_step(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr,
                             int64_t iter_begin, int32_t niter, int64_t archive_rows, void *stream) {
@@ -138,29 +188,44 @@ extern "C" int dreamzs_step_tempered(const dreamzs_config *cfg, const dreamzs_st
   return step_impl(cfg, st, tr, iter, 1, archive_rows, nullptr, 0, 0, stream, temperature);
 }
 
+static int64_t appends_between(int64_t t0, int64_t n, int64_t thin) {
+  if (n <= 0) return 0;
+  const int64_t first = ((t0 + thin - 1) / thin) * thin, last = t0 + n - 1;
+  return first > last ? 0 : (last - first) / thin + 1;
+}
+
+// multi: the launch spans several windows (persistent whitened window kernel, dreamzs_state.sync_ws); k0 = appends made
+// before it
 static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter_begin,
                      int32_t niter, int64_t archive_rows, const dreamzs_peers *peers, uint64_t wait_k, uint64_t publish_k,
-                     void *stream, const double *temperature) {
+                     void *stream, const double *temperature, bool multi, uint64_t k0) {
   int rc = check_cfg(cfg, st);
   if (rc != DREAMZS_OK) return rc;
   if (cfg->target_kind == DREAMZS_TARGET_EXTERNAL) return DREAMZS_E_UNSUPPORTED;   // use dreamzs_propose / dreamzs_accept
   if (!tr || !tr->trace || !tr->trace_logp || niter < 0 || iter_begin < 0) return DREAMZS_E_BADARG;
   if (tr->trace_offset < 0 || tr->trace_offset + niter > tr->trace_iters) return DREAMZS_E_BADARG;
   if (archive_rows < 2 * cfg->nDEpairs || archive_rows > st->Z_capacity_rows) return DREAMZS_E_BADARG;
-  // only the last iteration of a launch may append (the archive is read-only inside a launch)
-  for (int it = 0; it + 1 < niter; ++it)
-    if ((iter_begin + it) % cfg->history_thin == 0) return DREAMZS_E_BADARG;
-  if (niter > 0 && (iter_begin + niter - 1) % cfg->history_thin == 0 &&
-      archive_rows + cfg->nchains_global > st->Z_capacity_rows)
+  if (!multi) {
+    // only the last iteration of a launch may append (the archive is read-only inside a launch)
+    for (int it = 0; it + 1 < niter; ++it)
+      if ((iter_begin + it) % cfg->history_thin == 0) return DREAMZS_E_BADARG;
+  } else if (!st->sync_ws || appends_between(iter_begin, niter, cfg->history_thin) + 2 + 16 > st->sync_ws_words) return DREAMZS_E_BADARG;
+  if (archive_rows + appends_between(iter_begin, niter, cfg->history_thin) * cfg->nchains_global > st->Z_capacity_rows)
     return DREAMZS_E_BADARG;
   if (niter == 0 || cfg->nchains_local == 0) return DREAMZS_OK;
   StepParams P{};
   P.cfg = *cfg; P.st = *st; P.tr = *tr; P.iter_begin = iter_begin; P.niter = niter; P.archive_rows = archive_rows;
   P.all_flat = all_flat_hint(cfg);
+  if (multi) {
+    P.ww_sync = st->sync_ws; P.ww_k0 = k0;
+    // abort word + one counter per appending window of the span, zeroed in stream order
+    const size_t words = 16 + (size_t)appends_between(iter_begin, niter, cfg->history_thin) + 2;
+    if (cudaMemsetAsync(st->sync_ws, 0, words * sizeof(uint32_t), (cudaStream_t)stream) != cudaSuccess) { (void)cudaGetLastError(); return DREAMZS_E_LAUNCH; }
+  }
   if (temperature) {   // only the generic kernel scales the log-likelihood; the dense-Gaussian kernels assume T = 1
     P.temperature = temperature;
     P.cfg.flags |= DREAMZS_FLAG_GENERIC_KERNEL;
-    P.st.gauss_Y = nullptr; P.st.gauss_Q = nullptr;
+    P.st.gauss_Y = nullptr; P.st.gauss_Q = nullptr; P.st.gauss_L = nullptr; P.st.gauss_U = nullptr;
   }
   if (peers) {
     if (peers->world < 1 || peers->world > DREAMZS_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) return DREAMZS_E_BADARG;
@@ -233,11 +298,36 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
       return DREAMZS_E_LAUNCH;
     }
   }
+  // whitened window kernel with scratch words: ONE persistent launch per span of windows (up to the scratch size)
+  bool persistent = false;
+  if (st->sync_ws && st->sync_ws_words > 32 && !hook) {
+    StepParams Q{};
+    Q.cfg = *cfg; Q.st = *st; Q.all_flat = all_flat_hint(cfg);
+    persistent = check_cfg(cfg, st) == DREAMZS_OK && wwin_eligible(Q);
+  }
   while (t < end) {
     const int64_t nxt = ((t + thin - 1) / thin) * thin;          // first appending iteration >= t
     int64_t n = (end < nxt + 1 ? end : nxt + 1) - t;
     const bool burn = adapting && t <= adapt->crossover_burnin;
     if (burn) n = 1;
+    if (persistent && !burn) {
+      // as many whole windows as the scratch words allow
+      const int64_t maxwin = st->sync_ws_words - 32;
+      int64_t span = end - t;
+      if (appends_between(t, span, thin) > maxwin) span = (nxt + (maxwin - 1) * thin + 1) - t;
+      const int64_t napp = appends_between(t, span, thin);
+      w.trace_offset = tr->trace_offset + (t - iter_begin);
+      int rc = step_impl(cfg, st, &w, t, (int32_t)span, archive_rows, p2p ? peers : nullptr,
+                         (p2p && !waited) ? (uint64_t)appends_done : 0, 0, stream, nullptr, true, (uint64_t)appends_done);
+      if (rc != DREAMZS_OK) return rc;
+      ++nl;
+      waited = napp == 0 ? true : false;      // the next launch waits for the peers' last append of this one
+      if (!p2p) waited = true;
+      appends_done += napp;
+      archive_rows += napp * cfg->nchains_global;
+      t += span;
+      continue;
+    }
     w.trace_offset = tr->trace_offset + (t - iter_begin);
     const bool appends = (t + n - 1) % thin == 0;
     // with peers the launch itself waits for append #appends_done of the others (once) and publishes its own

@@ -82,26 +82,50 @@ __device__ __forceinline__ double nan_to_num(double x) {
   return x;
 }
 
-// Box-Muller on the four words of one block -> four normals (oracle/philox.py normal_vec)
+// Normal variates of the RNG contract (stream 2; recipe and rationale in oracle/philox.py normal_pairs32): Box-Muller
+// in float32 on 24-bit uniforms, written with operations IEEE-754 rounds identically on every machine (float add,
+// multiply, fma, sqrt with explicit round-to-nearest intrinsics, fixed Cephes coefficients), so that the kernels, the
+// C oracle and the numpy shim produce the same bits.  zeta (Dream.py:694) is N(0, 1e-12): float32 resolution is ample.
+__device__ __forceinline__ void normal_pair32(uint32_t w0, uint32_t w1, float &n0, float &n1) {
+  const float a = (float)((w0 >> 8) + 1u);                       // exact: <= 2^24
+  const uint32_t bits = __float_as_uint(a);
+  int E = (int)(bits >> 23) - 127;
+  float m = __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u);
+  if (m > 1.41421356f) { m = __fmul_rn(m, 0.5f); E += 1; }
+  const float t = __fadd_rn(m, -1.0f), z = __fmul_rn(t, t);
+  float P = 7.0376836292E-2f;
+  P = __fmaf_rn(P, t, -1.1514610310E-1f); P = __fmaf_rn(P, t, 1.1676998740E-1f); P = __fmaf_rn(P, t, -1.2420140846E-1f);
+  P = __fmaf_rn(P, t, 1.4249322787E-1f); P = __fmaf_rn(P, t, -1.6668057665E-1f); P = __fmaf_rn(P, t, 2.0000714765E-1f);
+  P = __fmaf_rn(P, t, -2.4999993993E-1f); P = __fmaf_rn(P, t, 3.3333331174E-1f);
+  float y = __fmul_rn(t, __fmul_rn(z, P));
+  y = __fmaf_rn(-0.5f, z, y);
+  const float logm = __fadd_rn(t, y);
+  const float L = __fmaf_rn((float)(E - 24), 0.6931471805599453f, logm);
+  const float val = __fmul_rn(-2.0f, L);
+  const float r = __fsqrt_rn(val > 0.0f ? val : 0.0f);
+  const int32_t w24 = (int32_t)(w1 >> 8);
+  const int32_t k = (w24 + (1 << 21)) >> 22;
+  const float g = __fmul_rn((float)(w24 - (k << 22)), 5.9604644775390625e-08f);   // 2^-24: exact
+  const float phi = __fmul_rn(g, 6.283185307179586f);
+  const float zz = __fmul_rn(phi, phi);
+  const float sp = __fmaf_rn(__fmaf_rn(-1.9515295891E-4f, zz, 8.3321608736E-3f), zz, -1.6666654611E-1f);
+  const float cp = __fmaf_rn(__fmaf_rn(2.443315711809948E-5f, zz, -1.388731625493765E-3f), zz, 4.166664568298827E-2f);
+  const float s = __fmaf_rn(__fmul_rn(phi, zz), sp, phi);
+  const float c = __fmaf_rn(__fmul_rn(zz, zz), cp, __fmaf_rn(-0.5f, zz, 1.0f));
+  const int q = k & 3;
+  const float cs = q == 0 ? c : q == 1 ? -s : q == 2 ? -c : s;
+  const float sn = q == 0 ? s : q == 1 ? c : q == 2 ? -s : -c;
+  n0 = __fmul_rn(r, cs); n1 = __fmul_rn(r, sn);
+}
+// the four words of one block -> four normals (float32 values; widened exactly where a double is wanted)
+__device__ __forceinline__ void normal4f(const uint4 w, float out[4]) {
+  normal_pair32(w.x, w.y, out[0], out[1]);
+  normal_pair32(w.z, w.w, out[2], out[3]);
+}
 __device__ __forceinline__ void normal4(const uint4 w, double out[4]) {
-#if defined(DZ_FAST_NORMAL) && DZ_FAST_NORMAL
-  // A/B builds only (default off; NOT the RNG contract): Box-Muller in float32 (24-bit normals, ~60 instead of ~250
-  // issue cycles per block).  With zeta = 1e-12 the difference to the fp64 normals is ~1e-19 on a state of O(1),
-  // i.e. below its last bit except for rare rounding flips; to be decided on measurements.
-  const float f0 = sqrtf(-2.0f * logf(((float)w.x + 1.0f) * (1.0f / 4294967296.0f)));
-  const float f1 = sqrtf(-2.0f * logf(((float)w.z + 1.0f) * (1.0f / 4294967296.0f)));
-  float fs0, fc0, fs1, fc1;
-  sincospif((float)w.y * (1.0f / 2147483648.0f), &fs0, &fc0);
-  sincospif((float)w.w * (1.0f / 2147483648.0f), &fs1, &fc1);
-  out[0] = (double)(f0 * fc0); out[1] = (double)(f0 * fs0); out[2] = (double)(f1 * fc1); out[3] = (double)(f1 * fs1);
-  return;
-#endif
-  const double r0 = sqrt(-2.0 * log(((double)w.x + 1.0) * (1.0 / 4294967296.0)));
-  const double r1 = sqrt(-2.0 * log(((double)w.z + 1.0) * (1.0 / 4294967296.0)));
-  double s0, c0, s1, c1;
-  sincospi((double)w.y * (1.0 / 2147483648.0), &s0, &c0);   // 2*pi*u == pi*(2u)
-  sincospi((double)w.w * (1.0 / 2147483648.0), &s1, &c1);
-  out[0] = r0 * c0; out[1] = r0 * s0; out[2] = r1 * c1; out[3] = r1 * s1;
+  float f[4];
+  normal4f(w, f);
+  out[0] = (double)f[0]; out[1] = (double)f[1]; out[2] = (double)f[2]; out[3] = (double)f[3];
 }
 
 // lane-group all-reduce (butterfly; every lane of the group ends with the same bits)
@@ -133,15 +157,17 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 // One thread: wait until every peer has published append #k (its rows are then in this rank's replica).
-__device__ __forceinline__ void peer_wait(const uint64_t *my_flags, int world, int rank, uint64_t k, int32_t *error) {
+// Returns false (and sets *error) when a peer has not published within DREAMZS_PEER_TIMEOUT_NS.
+__device__ __forceinline__ bool peer_wait(const uint64_t *my_flags, int world, int rank, uint64_t k, int32_t *error) {
   const uint64_t t0 = globaltimer_ns();
   for (int q = 0; q < world; ++q) {
     if (q == rank) continue;
     while (ld_acquire_sys(my_flags + q) < k) {
-      if (globaltimer_ns() - t0 > DREAMZS_PEER_TIMEOUT_NS) { atomicExch(error, 1); return; }
+      if (globaltimer_ns() - t0 > DREAMZS_PEER_TIMEOUT_NS) { atomicExch(error, 1); return false; }
       __nanosleep(100);
     }
   }
+  return true;
 }
 // The leader lane of a chain, after the chain's rows went to every replica and every storing lane executed
 // __threadfence_system(): count the chain; the last one publishes "append #k done" to every peer.

@@ -4,6 +4,13 @@
 
 namespace dreamzs {
 
+// shared-memory carve-up of the whitened window kernel (byte offsets; dreamzs_wwin_kernel.cuh wwin_layout)
+struct WwinLayout {
+  int32_t nch, nI, nK, ntilesL, ncolmax;
+  int32_t oL, oW, oJ, oN, oXs, oUs, oGam, oScr, oLogu, oGsn, oRows, oMbar, oMeta, oDpr, oMask, oProbs, oCst, oPool, npool, bytes;
+  uint32_t m_nch;   // ceil(2^20 / nch): division-free split of a task number
+};
+
 struct StepParams {
   dreamzs_config cfg;
   dreamzs_state st;
@@ -34,6 +41,10 @@ struct StepParams {
   long long *dbg;         // optional phase-timestamp buffer (dreamzs_debug_set_phase_buffer; profiling aid)
   int32_t gw_append;      // window kernel: the last iteration of the launch appends to the archive
   int32_t gw_refresh;     // window kernel: re-derive gauss_Y / gauss_Q from X at the start of the launch
+  WwinLayout ww_L;
+  int32_t ww_tc, ww_nb, ww_nsplit, ww_isplit[5];
+  uint32_t *ww_sync;      // != NULL: the launch spans several windows; word 0 abort flag, words 16.. chains that made append #j
+  uint64_t ww_k0;         // appends made before this launch (peer flags count appends from the start of the run)   // whitened window kernel: chains per CTA, iterations per batch, i-tile ranges of the products
   const double *temperature;   // [nchains_local] per-chain temperature T of astep(q0, T, ...) (Dream.py:193); NULL = 1
 };
 

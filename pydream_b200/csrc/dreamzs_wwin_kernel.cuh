@@ -1,0 +1,831 @@
+// Whitened window kernel for the dense-Gaussian target (BASELINE configs C2 / C5), sm_100a.
+//
+// One launch = one window of <= history_thin iterations (the archive is constant inside it) for TC chains per CTA,
+// 1024 threads.  A (chain, iteration) pair is a COLUMN.  Everything of Dream.astep that does not depend on the chain
+// state -- all draws, the archive rows, the jump dx = (e*gamma)*(z_r1 - z_r2) + zeta with its crossover mask -- is a
+// function of the Philox counters and of the archive, so it is produced for ALL columns of the window at once, flattened
+// over the CTA's threads; only the Markov chain itself is serial.
+//
+// The quadratic form is carried in WHITENED coordinates: invC = L L^T (Cholesky factor computed on the host in extended
+// precision), u = L^T x, Q(x) = |u|^2 and Q(x + dx) = |u + L^T dx|^2.  L is triangular, so the product costs d^2/2
+// FMAs per column instead of d^2, and the chain needs no second dot product.  The products of all columns,
+// DU = DX^T L, run on the fp64 tensor-core path (mma.sync m8n8k4 f64, SASS DMMA: same fp64 pipe as DFMA on B200 but
+// 8x fewer issue slots), triangular tiles only.
+//
+// Phases (CTA-wide barriers in between; `task` loops are flattened over all 1024 threads):
+//   S   scalar draws, one Philox block per (kind, column): snooker / CR / gamma level / gamma unity multinomials
+//       (Dream.py:542-599, 615), the two np.random.uniform() calls (:618, :993), the random.sample calls (:646-668);
+//       one thread per column assembles the decisions and stages the archive rows by TMA (cp.async.bulk, mbarrier
+//       complete_tx) straight into the column's slots
+//   V1  per (column, 4-dimension chunk): the crossover uniforms U (Dream.py:700) -> keep mask, d' (shared-memory atomic)
+//   V2  per (column, chunk): zeta (float32 Box-Muller of the RNG contract) and e, gamma from d', then
+//       J = (e*gamma)*(z_r1 - z_r2), dx = J + zeta in place of the staged rows (Dream.py:688-726)
+//   M   DU = DX^T L per 8-column tile on DMMA, results held in registers until every column has been read, then
+//       written in place of dx; a refresh window adds the chains' x as columns (u = L^T x)
+//   C   the chains (LPC lanes per chain): per iteration prop = (x + J) + zeta, Q' = |u + du|^2 by ONE reduction, the
+//       Metropolis test against the precomputed log u, state / trace / archive append.  The snooker move is linear in
+//       the state: dx = c (x - z), du = c (u - L^T z), so its column of M is L^T z.
+// RNG consumption, decisions and element-wise arithmetic are those of dreamzs_step_kernel / the oracle; only the
+// summation order of the quadratic form differs.
+#pragma once
+#include "dreamzs_gauss_kernel.cuh"
+
+namespace dreamzs {
+
+#ifndef DZ_WW_THREADS
+#define DZ_WW_THREADS 512
+#endif
+constexpr int WW_THREADS = DZ_WW_THREADS;   // A/B builds override (registers per thread = 65536 / threads)
+constexpr int WW_WARPS = WW_THREADS / 32;
+constexpr int WW_MAXI = WW_THREADS >= 1024 ? 8 : WW_THREADS >= 640 ? 10 : 16;   // i-tiles whose results one M warp holds in registers
+constexpr int WW_MAXSPLIT = 4;    // i-ranges an 8-column tile is split into
+
+__host__ __device__ inline int wwin_ntiles(int ld) {
+  const int nK = ld / 4, nI = (ld + 7) / 8;
+  int n = 0;
+  for (int I = 0; I < nI; ++I) n += max(0, nK - 2 * I);
+  return n;
+}
+// first tile of i-tile I in the packed factor: tiles (I, k = 2I .. nK-1), 32 doubles each in lane order
+__host__ __device__ inline int wwin_tile0(int nK, int I) { return I * nK - I * (I - 1); }
+
+// shared-memory carve-up (byte offsets), computed once on the host and passed with the launch parameters
+inline WwinLayout wwin_layout(int d, int ld, int TC, int NB, int ngamma) {
+  WwinLayout L;
+  L.nch = ld / 4; L.nK = ld / 4; L.nI = (ld + 7) / 8;
+  L.ntilesL = wwin_ntiles(ld);
+  L.ncolmax = TC * NB;
+  auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t o = 0;
+  L.oL = (int32_t)o;     o += up((size_t)L.ntilesL * 32 * 8);
+  L.oW = (int32_t)o;     o += up((size_t)(L.ncolmax + TC) * ld * 8);     // dx / z columns -> du; + TC refresh columns
+  L.oJ = (int32_t)o;     o += up((size_t)L.ncolmax * ld * 8);            // J = (e*gamma)*diff | snooker: z
+  L.oN = (int32_t)o;     o += up((size_t)L.ncolmax * ld * 4);            // float32 normals of zeta (0 where the dimension is reset)
+  L.oXs = (int32_t)o;    o += up((size_t)TC * ld * 8);
+  L.oUs = (int32_t)o;    o += up((size_t)TC * ld * 8);
+  L.oGam = (int32_t)o;   o += up((size_t)ngamma * d * 8);
+  L.oScr = (int32_t)o;   o += up((size_t)9 * L.ncolmax * 8);             // raw scalar draws [kind][column]
+  L.oLogu = (int32_t)o;  o += up((size_t)L.ncolmax * 8);
+  L.oGsn = (int32_t)o;   o += up((size_t)L.ncolmax * 8);
+  L.oRows = (int32_t)o;  o += up((size_t)L.ncolmax * 16);                // snooker z1, z2 row indices
+  L.oMbar = (int32_t)o;  o += up((size_t)(L.ncolmax + 1) * 8);
+  L.oMeta = (int32_t)o;  o += up((size_t)L.ncolmax * 4);
+  L.oDpr = (int32_t)o;   o += up((size_t)L.ncolmax * 4);
+  L.oMask = (int32_t)o;  o += up((size_t)L.ncolmax * L.nch);
+  L.oProbs = (int32_t)o; o += 40 * 8;                // [0,16) CR, [16,24) gamma level, 24 snooker, 26 unity, 32 abort flag
+  L.oCst = (int32_t)o;   o += up((size_t)TC * 4 * 8);
+  // pool of z1 - z2 rows for snooker columns (filled in V2, read by the chains): whatever shared memory is left, at most
+  // one slot per column; columns that find the pool full read z1, z2 from the archive inside the chain loop
+  L.oPool = (int32_t)o;
+  const size_t cap = 227 * 1024;
+  size_t slots = o < cap ? (cap - o) / ((size_t)ld * 8) : 0;
+  if (slots > (size_t)L.ncolmax) slots = (size_t)L.ncolmax;
+  L.npool = (int32_t)slots;
+  o += slots * (size_t)ld * 8;
+  L.bytes = (int32_t)o;
+  L.m_nch = ((1u << 20) + (uint32_t)L.nch - 1u) / (uint32_t)L.nch;
+  return L;
+}
+
+// x / div for x * div < 2^20 with m = ceil(2^20 / div) (exact in that range): the flattened task loops split a task
+// number into (column, chunk) and a column into (chain, iteration) without integer division
+__device__ __forceinline__ int fdiv20(int x, uint32_t m) { return (int)(((uint32_t)x * m) >> 20); }
+__device__ __forceinline__ uint32_t fdiv20_magic(int div) { return ((1u << 20) + (uint32_t)div - 1u) / (uint32_t)div; }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Philox4x32-10 inlined (the flattened V passes are straight-line code; two independent blocks interleave)
+__device__ __forceinline__ uint4 philox_inl(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+template <int LPC>
+__device__ __forceinline__ double lsum(double v) {
+#pragma unroll
+  for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Can archive row r be read?  Rows below the launch's archive size always can.  A row appended DURING this launch belongs
+// to append block j = (r - archive_rows) / nchains_global and to the chain (r - archive_rows) % nchains_global: it is there
+// once every local chain has made append j (counters[j] == nchains_local; each chain counts itself after its row is
+// globally visible) or, for a chain of peer rank q, once q has published append ww_k0 + j + 1 (the flag is written after
+// q's rows have reached this replica).  Gives up after DREAMZS_PEER_TIMEOUT_NS or when another CTA has aborted.
+struct RowWait {      // what row_ready needs of the launch parameters (by value: the parameter block stays in constant memory)
+  int64_t archive_rows;
+  int32_t nchains_global, chain_begin, nchains_local;
+  uint64_t k0;
+  const uint64_t *my_flags;
+  int32_t *peer_error;
+  const uint32_t *counters;
+  volatile int32_t *status;
+};
+__device__ __noinline__ bool row_wait(const RowWait w, int64_t r) {
+  const int64_t off = r - w.archive_rows;
+  const int j = (int)(off / w.nchains_global);
+  const int owner = (int)(off - (int64_t)j * w.nchains_global);
+  const bool local = owner >= w.chain_begin && owner < w.chain_begin + w.nchains_local;
+  const int q = local ? 0 : owner / w.nchains_local;
+  const uint64_t k = w.k0 + (uint64_t)j + 1u;
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+    if (local ? ld_acquire_gpu_u32(w.counters + j) >= (uint32_t)w.nchains_local : ld_acquire_sys(w.my_flags + q) >= k) return true;
+    if (*w.status != 0) return false;
+    if (globaltimer_ns() - t0 > DREAMZS_PEER_TIMEOUT_NS) {
+      atomicExch(const_cast<int32_t *>(w.status), 1);
+      if (w.peer_error) atomicExch(w.peer_error, 1);
+      return false;
+    }
+    __nanosleep(200);
+  }
+}
+__device__ __forceinline__ bool row_ready(const RowWait &w, int64_t r) {
+  return (r < w.archive_rows || !w.counters) ? true : row_wait(w, r);
+}
+__device__ __forceinline__ bool rows_ready(const RowWait &w, int64_t ra, int64_t rb, int64_t rc) {
+  bool ok = row_ready(w, ra);
+  ok = row_ready(w, rb) && ok;
+  if (rc >= 0) ok = row_ready(w, rc) && ok;
+  return ok;
+}
+
+#ifndef DZ_WW_MINBLOCKS
+#define DZ_WW_MINBLOCKS 1
+#endif
+
+template <int LPC>
+__global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kernel(const StepParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int d = P.cfg.ndim, ld = P.cfg.ld, TC = P.ww_tc, NB = P.ww_nb;
+  const WwinLayout &L = P.ww_L;
+  const int nch = L.nch, nK = L.nK;
+  double *Lf = reinterpret_cast<double *>(smem_raw + L.oL), *Wc = reinterpret_cast<double *>(smem_raw + L.oW);
+  double *Jc = reinterpret_cast<double *>(smem_raw + L.oJ);
+  float *Nz = reinterpret_cast<float *>(smem_raw + L.oN);
+  double *Xs = reinterpret_cast<double *>(smem_raw + L.oXs), *Us = reinterpret_cast<double *>(smem_raw + L.oUs);
+  double *gam = reinterpret_cast<double *>(smem_raw + L.oGam);
+  uint2 *scr = reinterpret_cast<uint2 *>(smem_raw + L.oScr);
+  double *logu = reinterpret_cast<double *>(smem_raw + L.oLogu), *gsn = reinterpret_cast<double *>(smem_raw + L.oGsn);
+  int64_t *rows = reinterpret_cast<int64_t *>(smem_raw + L.oRows);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + L.oMbar);   // [0, ncolmax) columns, [ncolmax] the factor
+  uint32_t *meta = reinterpret_cast<uint32_t *>(smem_raw + L.oMeta);
+  int *dpr = reinterpret_cast<int *>(smem_raw + L.oDpr);
+  unsigned char *maskb = smem_raw + L.oMask;
+  double *probs = reinterpret_cast<double *>(smem_raw + L.oProbs), *cst = reinterpret_cast<double *>(smem_raw + L.oCst);
+  double *pool = reinterpret_cast<double *>(smem_raw + L.oPool);
+  int *pool_n = reinterpret_cast<int *>(probs + 34);          // snooker columns of the batch that hold a pool slot
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double logF = P.st.target_table[0];
+  int dbg_n = 0;
+#define WW_STAMP() do { if (P.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 60) P.dbg[dbg_n] = clock64(); ++dbg_n; } while (0)
+  WW_STAMP();   // 0: kernel entry
+
+  const uint32_t row_bytes = (uint32_t)ld * 8u;
+  const uint32_t s0 = P.cfg.snooker != 0 ? 1u : 0u;   // multinomial call number of the CR draw
+  const uint32_t k0 = (uint32_t)P.cfg.seed, k1 = (uint32_t)(P.cfg.seed >> 32);
+  const int ngroups = (P.cfg.nchains_local + TC - 1) / TC;          // groups of TC chains; a CTA takes groups blockIdx.x, + gridDim.x, ...
+  const bool resident = ngroups <= (int)gridDim.x;                  // one group per CTA: chain states stay in shared memory
+  volatile int32_t *status = reinterpret_cast<volatile int32_t *>(P.ww_sync);     // word 0: != 0 aborts the launch
+  uint32_t *counters = P.ww_sync ? P.ww_sync + 16 : nullptr;                     // chains that have made append #j of this launch
+
+  // ---- prologue: one TMA bulk copy brings the packed factor; tables -> shared memory
+  if (tid <= L.ncolmax) mbar_init(mbar + tid, 1);
+  if (tid < 40) {
+    double v = 0.0;
+    if (tid < 16) v = tid < P.cfg.nCR ? P.st.cr_probs[tid] : 0.0;
+    else if (tid < 24) v = tid - 16 < P.cfg.ngamma ? P.st.gamma_probs[tid - 16] : 0.0;
+    else if (tid == 24) v = P.cfg.snooker;
+    else if (tid == 26) v = P.cfg.p_gamma_unity;
+    probs[tid] = v;
+  }
+  for (int i = tid; i < L.ncolmax; i += WW_THREADS) meta[i] = 0;      // bit 11 carries a column slot's mbarrier phase
+  for (int i = tid; i < P.cfg.ngamma * d; i += WW_THREADS) {   // gamma_table[level][0][:] (one DE pair)
+    const int lv = i / d;
+    gam[i] = P.st.gamma_table[(size_t)lv * P.cfg.nDEpairs * d + (i - lv * d)];
+  }
+  __syncthreads();
+  if (tid == 32) {
+    // a peer's append has not arrived within the timeout (in an earlier launch, or now): leave everything untouched,
+    // the host raises (DreamEngine.check_peers)
+    bool bad = (P.peer_error && *reinterpret_cast<volatile int32_t *>(P.peer_error) != 0) || (status && *status != 0);
+    if (!bad && P.wait_k) bad = !peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);   // the peers' rows have landed
+    probs[32] = bad ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (probs[32] != 0.0) return;
+  if (tid == 0) {
+    fence_proxy_async();
+    const uint32_t bytes = (uint32_t)L.ntilesL * 256u;
+    mbar_expect_tx(mbar + L.ncolmax, bytes);
+    tma_load_row(Lf, P.st.gauss_L, bytes, mbar + L.ncolmax);
+  }
+  WW_STAMP();   // 1: prologue done
+  bool factor_ready = false;
+
+  // ================================================================ windows of the launch (pydream/core.py:103-122)
+  // A window ends at an appending iteration (t % history_thin == 0); the archive it samples is the one of the launch's
+  // start plus the appends of the windows before it.  CTAs do not synchronise per window: a column whose sampled row was
+  // appended during THIS launch waits for the chains that write that block (counters / peer flags), nothing else waits.
+  const int64_t t_end = P.iter_begin + P.niter;
+  const int64_t thin = P.cfg.history_thin;
+  int blk = 0;                                    // appends made by the windows before the current one (this launch)
+  bool first_window = true;
+  for (int64_t wt0 = P.iter_begin; wt0 < t_end;) {
+   const int64_t nxt = ((wt0 + thin - 1) / thin) * thin;            // first appending iteration >= wt0
+   const int wn = (int)((t_end < nxt + 1 ? t_end : nxt + 1) - wt0); // iterations of this window
+   const bool w_append = (wt0 + wn - 1) % thin == 0;
+   const bool w_refresh = wt0 == 0 || ((wt0 - 1) % thin == 0 && ((wt0 - 1) / thin) % DREAMZS_GAUSS_REFRESH_WINDOWS == 0);
+   const bool last_window = wt0 + wn >= t_end;
+   const int64_t M = P.archive_rows + (int64_t)blk * P.cfg.nchains_global;   // archive rows this window samples
+   const int64_t trace_row0 = P.tr.trace_offset + (wt0 - P.iter_begin);
+   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  const int cta_chain0 = grp * TC;
+  const int nch_cta = min(TC, P.cfg.nchains_local - cta_chain0);   // chains of this group
+  if (!resident || first_window) {   // chain states -> shared memory
+    for (int i = tid; i < nch_cta * nch; i += WW_THREADS) {
+      const int cs = fdiv20(i, L.m_nch), q = i - cs * nch;
+      const int c_local = cta_chain0 + cs;
+      const double2 *xr = reinterpret_cast<const double2 *>(P.st.X + (size_t)c_local * ld + 4 * q);
+      double2 *xd = reinterpret_cast<double2 *>(Xs + (size_t)cs * ld + 4 * q);
+      xd[0] = xr[0]; xd[1] = xr[1];
+      if (!w_refresh) {
+        const double2 *ur = reinterpret_cast<const double2 *>(P.st.gauss_U + (size_t)c_local * ld + 4 * q);
+        double2 *ud = reinterpret_cast<double2 *>(Us + (size_t)cs * ld + 4 * q);
+        ud[0] = ur[0]; ud[1] = ur[1];
+      }
+    }
+    if (tid < nch_cta) {
+      cst[tid * 4 + 1] = P.st.last_prior[cta_chain0 + tid];
+      cst[tid * 4 + 2] = P.st.last_like[cta_chain0 + tid];
+    }
+    __syncthreads();
+  }
+
+  int done = 0;
+  for (int batch = 0; done < wn; ++batch) {
+    const int nb = min(NB, wn - done);
+    const int ncol = nch_cta * nb;                 // columns of this batch: col = chain * nb + iteration
+    const uint32_t m_nb = fdiv20_magic(nb), m_nch = L.m_nch;
+    const bool do_refresh = w_refresh && batch == 0;
+    // ================================================================ S: scalar draws (thread per (kind, column))
+    for (int task = tid; task < 9 * ncol; task += WW_THREADS) {
+      int kind = 0, col = task;
+      while (col >= ncol) { col -= ncol; ++kind; }
+      const int ch = fdiv20(col, m_nb), itb = col - ch * nb;
+      const uint32_t iter = (uint32_t)(wt0 + done + itb);
+      const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
+      uint32_t call = 0, st = ST_MULTINOMIAL;
+      const double *pp = probs + 24;
+      int n = 2;
+      if (kind == 1) { call = s0; pp = probs; n = P.cfg.nCR; }
+      else if (kind == 2) { call = s0 + 1; pp = probs + 16; n = P.cfg.ngamma; }
+      else if (kind == 3) { call = s0 + 2; pp = probs + 26; }
+      else if (kind == 4) { st = ST_UNIFORM_SCAL; }
+      else if (kind == 5) { call = 1; st = ST_UNIFORM_SCAL; }
+      else if (kind >= 6) { call = (uint32_t)(kind - 6); st = ST_SAMPLE; }
+      const uint4 w = philox_inl(0u, (call << 3) | st, iter, c_global, k0, k1);
+      uint2 out = make_uint2(w.x, w.y);
+      if (kind < 4) {          // np.random.multinomial(1, p): inverse CDF on a running sum
+        const double u = u53_of(w.x, w.y);
+        double acc = 0.0;
+        int idx = n - 1;
+        bool found = false;
+        for (int j = 0; j < n; ++j) {
+          acc = acc + pp[j];
+          if (!found && u < acc) { idx = j; found = true; }
+        }
+        out.x = (uint32_t)idx;
+      }
+      if (kind == 4 || kind == 5) {   // both candidates for the Metropolis uniform: log u now, off the per-column path
+        const double lg = log(u53_of(w.x, w.y));
+        if (kind == 5) out = make_uint2((uint32_t)__double2loint(lg), (uint32_t)__double2hiint(lg));
+        else reinterpret_cast<double *>(logu)[col] = lg;
+      }
+      scr[kind * L.ncolmax + col] = out;
+    }
+    if (tid == 0) *pool_n = 0;
+    __syncthreads();
+    // ---- one thread per column: decisions, log u, archive rows -> TMA
+    const RowWait rw = {P.archive_rows, P.cfg.nchains_global, P.cfg.chain_begin, P.cfg.nchains_local, P.ww_k0, P.my_flags,
+                        P.peer_error, counters, status};
+    for (int col = tid; col < ncol; col += WW_THREADS) {
+      const uint2 q0 = scr[col], q1 = scr[L.ncolmax + col], q2 = scr[2 * L.ncolmax + col], q3 = scr[3 * L.ncolmax + col];
+      const uint2 u4 = scr[4 * L.ncolmax + col], u5 = scr[5 * L.ncolmax + col];
+      const uint2 r6 = scr[6 * L.ncolmax + col], r7 = scr[7 * L.ncolmax + col], r8 = scr[8 * L.ncolmax + col];
+      const bool snk = (s0 != 0u) && q0.x == 0u;
+      // meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set in V2), 10 "not unity"
+      const uint32_t ph = meta[col] & 2048u;                 // mbarrier phase this use of the slot completes (bit 11)
+      uint32_t mt = q1.x | (q2.x << 4) | (snk ? 256u : 0u) | (q3.x != 0u ? 1024u : 0u) | (ph ^ 2048u);
+      // Metropolis uniform: the 2nd np.random.uniform() after a snooker gamma, else the 1st (its log is in place)
+      if (snk) logu[col] = __hiloint2double((int)u5.y, (int)u5.x);
+      double *js = Jc + (size_t)col * ld, *ws = Wc + (size_t)col * ld;
+      mbar_expect_tx(mbar + col, 2u * row_bytes);
+      if (!snk) {
+        const int64_t ra = (int64_t)(((uint64_t)r6.x * (uint64_t)M) >> 32);
+        int64_t rb = (int64_t)(((uint64_t)r6.y * (uint64_t)(M - 1)) >> 32);
+        if (rb >= ra) rb += 1;
+        if (!rows_ready(rw, ra, rb, -1)) probs[32] = 1.0;
+        fence_proxy_async();   // the slots' earlier generic-proxy accesses and the acquired rows are ordered before the async copies
+        tma_load_row(js, P.st.Z + (size_t)ra * ld, row_bytes, mbar + col);   // z_r1 -> J slot
+        tma_load_row(ws, P.st.Z + (size_t)rb * ld, row_bytes, mbar + col);   // z_r2 -> W slot
+      } else {
+        const double g = 1.2 + (2.2 - 1.2) * u53_of(u4.x, u4.y);             // snooker gamma, Dream.py:618
+        gsn[col] = g;
+        if (g == 1.0) mt |= 512u;
+        const int64_t rz = (int64_t)(((uint64_t)r6.x * (uint64_t)M) >> 32);
+        rows[2 * col] = (int64_t)(((uint64_t)r7.x * (uint64_t)M) >> 32);
+        rows[2 * col + 1] = (int64_t)(((uint64_t)r8.x * (uint64_t)M) >> 32);
+        const int slot = atomicAdd(pool_n, 1);                               // z1 - z2 goes to the pool when a slot is left
+        dpr[col] = slot < L.npool ? slot : -1;
+        if (!rows_ready(rw, rz, rows[2 * col], rows[2 * col + 1])) probs[32] = 1.0;
+        fence_proxy_async();
+        tma_load_row(js, P.st.Z + (size_t)rz * ld, row_bytes, mbar + col);   // z -> J slot and W slot (-> L^T z)
+        tma_load_row(ws, P.st.Z + (size_t)rz * ld, row_bytes, mbar + col);
+      }
+      meta[col] = mt;
+      if (!snk) dpr[col] = 0;
+    }
+    __syncthreads();
+    WW_STAMP();   // +0: rows requested
+    // ================================================================ V1: crossover uniforms -> keep mask, d'
+    const int ntask = ncol * nch;
+    for (int task = tid; task < ntask; task += WW_THREADS) {
+      const int col = fdiv20(task, m_nch), q = task - col * nch;
+      const uint32_t mt = meta[col];
+      if (mt & 256u) continue;
+      const int ch = fdiv20(col, m_nb), itb = col - ch * nb;
+      const uint32_t iter = (uint32_t)(wt0 + done + itb);
+      const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
+      const uint4 wu = philox_inl((uint32_t)q, (1u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
+      // U = w 2^-32 exactly, so U < CR <=> w < ceil(CR 2^32) and U > CR <=> w > floor(CR 2^32)
+      const double CRs = ((double)((mt & 15u) + 1u) / (double)P.cfg.nCR) * 4294967296.0;
+      const uint64_t t_lt = (uint64_t)ceil(CRs), t_gt = (uint64_t)floor(CRs);
+      const uint32_t wv[4] = {wu.x, wu.y, wu.z, wu.w};
+      unsigned reset = 0;
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (4 * q + j < d) {
+          cnt += ((uint64_t)wv[j] < t_lt);
+          if ((uint64_t)wv[j] > t_gt) reset |= 1u << j;
+        } else reset |= 1u << j;
+      }
+      maskb[task] = (unsigned char)reset;
+      if (cnt) atomicAdd(dpr + col, cnt);
+    }
+    __syncthreads();
+    WW_STAMP();   // +1: masks
+    // ================================================================ V2: zeta, e, gamma -> J, dx in place of the rows
+    for (int task = tid; task < ntask; task += WW_THREADS) {
+      const int col = fdiv20(task, m_nch), q = task - col * nch;
+      const uint32_t mt = meta[col];
+      if (mt & 256u) {   // snooker column: z1 - z2 (Dream.py:810) -> pool slot; z / L^T z arrive by TMA
+        const int slot = dpr[col];
+        if (slot >= 0) {
+          const double *z1 = P.st.Z + (size_t)rows[2 * col] * ld + 4 * q, *z2 = P.st.Z + (size_t)rows[2 * col + 1] * ld + 4 * q;
+          const double2 p01 = __ldg(reinterpret_cast<const double2 *>(z1)), p23 = __ldg(reinterpret_cast<const double2 *>(z1) + 1);
+          const double2 q01 = __ldg(reinterpret_cast<const double2 *>(z2)), q23 = __ldg(reinterpret_cast<const double2 *>(z2) + 1);
+          double2 *bs = reinterpret_cast<double2 *>(pool + (size_t)slot * ld + 4 * q);
+          bs[0] = make_double2(p01.x - q01.x, p01.y - q01.y);
+          bs[1] = make_double2(p23.x - q23.x, p23.y - q23.y);
+        }
+        mbar_wait(mbar + col, ((mt >> 11) & 1u) ^ 1u);
+        continue;
+      }
+      const int ch = fdiv20(col, m_nb), itb = col - ch * nb;
+      const uint32_t iter = (uint32_t)(wt0 + done + itb);
+      const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
+      // two independent Philox blocks, interleaved by the compiler
+      const uint4 wn = philox_inl((uint32_t)q, (0u << 3) | ST_NORMAL, iter, c_global, k0, k1);
+      const uint4 we = philox_inl((uint32_t)q, (0u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
+      float nz[4];
+      normal4f(wn, nz);
+      const uint32_t wev[4] = {we.x, we.y, we.z, we.w};
+      const unsigned reset = maskb[task];
+      const int dprime = dpr[col];
+      double gamma = 1.0;
+      if (mt & 1024u) gamma = gam[((mt >> 4) & 15u) * d + (dprime >= 1 ? dprime - 1 : d - 1)];
+      if (q == 0 && gamma == 1.0) atomicOr(meta + col, 512u);
+      double *js = Jc + (size_t)col * ld + 4 * q, *ws = Wc + (size_t)col * ld + 4 * q;
+      float *ns = Nz + (size_t)col * ld + 4 * q;
+      mbar_wait(mbar + col, ((mt >> 11) & 1u) ^ 1u);
+      const double2 a01 = *reinterpret_cast<const double2 *>(js), a23 = *reinterpret_cast<const double2 *>(js + 2);
+      const double2 b01 = *reinterpret_cast<const double2 *>(ws), b23 = *reinterpret_cast<const double2 *>(ws + 2);
+      const double diff[4] = {a01.x - b01.x, a01.y - b01.y, a23.x - b23.x, a23.y - b23.y};
+      double J[4], dl[4];
+      float nk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool keep = !((reset >> j) & 1u);
+        const double e = (-P.cfg.lamb + (P.cfg.lamb - (-P.cfg.lamb)) * u32_of(wev[j])) + 1;
+        const double zt = 0.0 + P.cfg.zeta * (double)nz[j];
+        J[j] = keep ? (e * gamma) * diff[j] : 0.0;
+        nk[j] = keep ? __fadd_rn(nz[j], 0.0f) : 0.0f;      // -0 -> +0: the chain then needs no `0.0 +` (np.random.normal(0, zeta))
+        dl[j] = keep ? J[j] + zt : 0.0;
+      }
+      *reinterpret_cast<double2 *>(js) = make_double2(J[0], J[1]); *reinterpret_cast<double2 *>(js + 2) = make_double2(J[2], J[3]);
+      *reinterpret_cast<double2 *>(ws) = make_double2(dl[0], dl[1]); *reinterpret_cast<double2 *>(ws + 2) = make_double2(dl[2], dl[3]);
+      *reinterpret_cast<float4 *>(ns) = make_float4(nk[0], nk[1], nk[2], nk[3]);
+    }
+    if (do_refresh) {   // refresh columns: x of every chain, right after the batch's columns
+      for (int i = tid; i < nch_cta * nch; i += WW_THREADS) {
+        const int cs = fdiv20(i, m_nch), q = i - cs * nch;
+        double2 *wd = reinterpret_cast<double2 *>(Wc + (size_t)(ncol + cs) * ld + 4 * q);
+        const double2 *xs = reinterpret_cast<const double2 *>(Xs + (size_t)cs * ld + 4 * q);
+        wd[0] = xs[0]; wd[1] = xs[1];
+      }
+    }
+    if (!factor_ready) { mbar_wait(mbar + L.ncolmax, 0); factor_ready = true; }   // the factor has landed
+    __syncthreads();
+    if (probs[32] != 0.0) return;   // a wait for appended rows timed out (or another CTA aborted): give up, the host raises
+    WW_STAMP();   // +2: columns generated
+    // ================================================================ M: DU = DX^T L on DMMA
+    // unit = (8-column tile, range of i-tiles) -> one warp (the host picks TC, NB and the split so that units <= 32 and a
+    // range holds <= WW_MAXI i-tiles).  D fragment: lane l holds du[column l/4][8 I + 2 (l%4) + {0,1}].
+    {
+      const int ncols_total = ncol + (do_refresh ? nch_cta : 0);
+      const int NT = (ncols_total + 7) / 8;
+      const int nsplit = P.ww_nsplit;
+      const int l4 = lane >> 2, lm = lane & 3;
+      const bool mwarp = warp < NT * nsplit;
+      const int nt = warp / nsplit, sp = warp - nt * nsplit;
+      const int Ia = P.ww_isplit[mwarp ? sp : 0], Ib = P.ww_isplit[mwarp ? sp + 1 : 0];
+      double acc[WW_MAXI][2];
+#pragma unroll
+      for (int t = 0; t < WW_MAXI; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+      if (mwarp) {
+        const int crow = min(nt * 8 + l4, ncols_total - 1);     // padding rows alias the last column (results dropped)
+        const double *arow = Wc + (size_t)crow * ld + lm;
+#pragma unroll
+        for (int t = 0; t < WW_MAXI; t += 2) {
+          const int I0 = Ia + t, I1 = I0 + 1;
+          if (I0 < Ib) {
+            const bool two = I1 < Ib;
+            const int ka = 2 * I0, kb = two ? min(2 * I1, nK) : nK;   // k in [ka, kb) feeds I0 only, [kb, nK) feeds both
+            const double *b0 = Lf + (size_t)wwin_tile0(nK, I0) * 32 + lane;
+            const double *b1 = Lf + (size_t)wwin_tile0(nK, two ? I1 : I0) * 32 + lane;
+#pragma unroll 1
+            for (int k = ka; k < kb; ++k) dmma884(acc[t][0], acc[t][1], arow[4 * k], b0[(size_t)(k - ka) * 32]);
+            if (two) {
+#pragma unroll 2
+              for (int k = kb; k < nK; ++k) {
+                const double a = arow[4 * k];
+                dmma884(acc[t][0], acc[t][1], a, b0[(size_t)(k - ka) * 32]);
+                dmma884(acc[t + 1][0], acc[t + 1][1], a, b1[(size_t)(k - kb) * 32]);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();   // every column has been read: the products may now overwrite dx in place
+      WW_STAMP();   // +3: products computed
+      if (mwarp) {
+        const int c = nt * 8 + l4;
+        if (c < ncols_total) {
+          double *wrow = Wc + (size_t)c * ld + 2 * lm;
+#pragma unroll
+          for (int t = 0; t < WW_MAXI; ++t) {
+            const int I = Ia + t;
+            if (I < Ib && 8 * I + 2 * lm < ld) *reinterpret_cast<double2 *>(wrow + 8 * I) = make_double2(acc[t][0], acc[t][1]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    WW_STAMP();   // +4: products written
+    // ================================================================ C: the chains (LPC lanes per chain)
+    {
+      constexpr int CPW = 32 / LPC;                     // chains per warp
+      const int sub = lane / LPC, g = lane - sub * LPC;
+      const int cs = warp * CPW + sub;                  // chain slot in the CTA
+      const bool cwarp = warp * CPW < nch_cta;
+      if (cwarp) {
+        const bool valid = cs < nch_cta;
+        const int csv = valid ? cs : nch_cta - 1;       // lanes of a missing chain shadow the last one (no stores)
+        const int c_local = cta_chain0 + csv;
+        const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + c_local);
+        const int i0 = 4 * g;
+        const bool own = i0 < ld;
+        double x0[4] = {0, 0, 0, 0}, u0[4] = {0, 0, 0, 0};
+        double last_prior = cst[csv * 4 + 1], last_like = cst[csv * 4 + 2];
+        if (own) {
+          const double2 a = *reinterpret_cast<const double2 *>(Xs + csv * ld + i0), b = *reinterpret_cast<const double2 *>(Xs + csv * ld + i0 + 2);
+          x0[0] = a.x; x0[1] = a.y; x0[2] = b.x; x0[3] = b.y;
+          const double *us = do_refresh ? Wc + (size_t)(ncol + csv) * ld + i0 : Us + csv * ld + i0;
+          const double2 c = *reinterpret_cast<const double2 *>(us), e = *reinterpret_cast<const double2 *>(us + 2);
+          u0[0] = c.x; u0[1] = c.y; u0[2] = e.x; u0[3] = e.y;
+        }
+        double ntn_last = nan_to_num(1.0 * last_like + last_prior);
+        const double zeta = P.cfg.zeta;
+        double *trow_ptr = P.tr.trace + ((size_t)c_local * P.tr.trace_iters + (trace_row0 + done)) * ld + i0;
+        double *lrow_ptr = P.tr.trace_logp + (size_t)c_local * P.tr.trace_iters + (trace_row0 + done);
+        uint32_t *drow_ptr = P.tr.decisions ? P.tr.decisions + (size_t)c_local * P.tr.trace_iters + (trace_row0 + done) : nullptr;
+#pragma unroll 1
+        for (int itb = 0; itb < nb; ++itb) {
+          const int col = csv * nb + itb;
+          const uint32_t mt = meta[col];
+          const double lu = logu[col];
+          const int run_snooker = (mt >> 8) & 1;
+          const double *js = Jc + (size_t)col * ld + i0, *ws = Wc + (size_t)col * ld + i0;
+          double prop[4] = {0, 0, 0, 0}, un[4] = {0, 0, 0, 0}, snk_logp = 0.0, cur = 0.0;
+          if (own) {
+            // prop = q0 + e*gamma*diff + zeta (Dream.py:717); Q(prop) = |u + L^T dx|^2
+            const double2 j01 = *reinterpret_cast<const double2 *>(js), j23 = *reinterpret_cast<const double2 *>(js + 2);
+            const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
+            const float4 nn = *reinterpret_cast<const float4 *>(Nz + (size_t)col * ld + i0);
+            // (zeta = 0.0 + zeta * n: the stored normals carry no -0, so the product needs no `0.0 +`)
+            prop[0] = (x0[0] + j01.x) + zeta * (double)nn.x;
+            prop[1] = (x0[1] + j01.y) + zeta * (double)nn.y;
+            prop[2] = (x0[2] + j23.x) + zeta * (double)nn.z;
+            prop[3] = (x0[3] + j23.y) + zeta * (double)nn.w;
+            un[0] = u0[0] + w01.x; un[1] = u0[1] + w01.y; un[2] = u0[2] + w23.x; un[3] = u0[3] + w23.y;
+          }
+          if (__any_sync(0xffffffffu, run_snooker)) {
+            // snooker_update, Dream.py:827-835 (single-point form); J slot = z, W slot = L^T z, z1 - z2 read from the archive
+            double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+            if (run_snooker && own) {
+              const double2 j01 = *reinterpret_cast<const double2 *>(js), j23 = *reinterpret_cast<const double2 *>(js + 2);
+              a[0] = j01.x; a[1] = j01.y; a[2] = j23.x; a[3] = j23.y;
+              const int slot = dpr[col];
+              if (slot >= 0) {      // z1 - z2 staged by V2
+                const double2 b01 = *reinterpret_cast<const double2 *>(pool + (size_t)slot * ld + i0);
+                const double2 b23 = *reinterpret_cast<const double2 *>(pool + (size_t)slot * ld + i0 + 2);
+                b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
+              } else {              // pool full: read the two rows here
+                const double *z1 = P.st.Z + (size_t)rows[2 * col] * ld + i0, *z2 = P.st.Z + (size_t)rows[2 * col + 1] * ld + i0;
+                const double2 p01 = __ldg(reinterpret_cast<const double2 *>(z1)), p23 = __ldg(reinterpret_cast<const double2 *>(z1) + 1);
+                const double2 q01 = __ldg(reinterpret_cast<const double2 *>(z2)), q23 = __ldg(reinterpret_cast<const double2 *>(z2) + 1);
+                b[0] = p01.x - q01.x; b[1] = p01.y - q01.y; b[2] = p23.x - q23.x; b[3] = p23.y - q23.y;
+              }
+            }
+            const double gamma = gsn[col];
+            double v[4];
+            double D = 0.0, S = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[j] = (i0 + j < d) ? x0[j] - a[j] : 0.0;
+              D = fma(v[j], v[j], D);
+              b[j] = b[j] * v[j];
+            }
+            D = lsum<LPC>(D);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S += (D != 0) ? b[j] / D : 0.0;
+            const double sc = nan_to_num(lsum<LPC>(S));
+            const double cg = gamma * sc;
+            double nn = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool okd = i0 + j < d;
+              const double o = okd ? x0[j] + gamma * (sc * v[j]) : 0.0;
+              const double ww = okd ? o - a[j] : 0.0;
+              nn = fma(ww, ww, nn);
+              if (run_snooker) prop[j] = o;
+            }
+            nn = lsum<LPC>(nn);
+            if (run_snooker) {
+              if (own) {   // L^T dx = c (u - L^T z)
+                const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
+                un[0] = u0[0] + cg * (u0[0] - w01.x); un[1] = u0[1] + cg * (u0[1] - w01.y);
+                un[2] = u0[2] + cg * (u0[2] - w23.x); un[3] = u0[3] + cg * (u0[3] - w23.y);
+              }
+              const double norm = sqrt(nn);
+              snk_logp = (norm != 0 ? log(norm) : 0.0) * (d - 1);
+              const double n0 = sqrt(D);
+              cur = (n0 != 0 ? log(n0) : 0.0) * (d - 1);
+            }
+          }
+          double part = fma(un[1], un[1], un[0] * un[0]) + fma(un[3], un[3], un[2] * un[2]);
+          int anydiff = (prop[0] != x0[0]) | (prop[1] != x0[1]) | (prop[2] != x0[2]) | (prop[3] != x0[3]);
+          if (LPC == 32) anydiff = __any_sync(0xffffffffu, anydiff);
+          else {
+            const unsigned bal = __ballot_sync(0xffffffffu, anydiff);
+            anydiff = ((bal >> (sub * LPC)) & ((LPC == 32) ? 0xffffffffu : ((1u << LPC) - 1u))) != 0u;
+          }
+          const double Qn = lsum<LPC>(part);
+          const double q_like = logF - .5 * Qn;
+          // mr = nan_to_num(q_logp) - nan_to_num(last_logp) (Dream.py:334); nan_to_num is the identity on finite values,
+          // which one comparison establishes (|x| <= DBL_MAX is false for inf and nan)
+          double mr = q_like - ntn_last;
+          if (!(fabs(q_like) <= DBL_MAX)) mr = nan_to_num(q_like) - ntn_last;
+          if (run_snooker) mr = nan_to_num((q_like + snk_logp) - ((1.0 * last_like + last_prior) + cur));   // Dream.py:326-332
+          const bool accepted = (fabs(mr) <= DBL_MAX) && lu < mr;                          // metrop_select, Dream.py:980-998
+          const int changed = accepted && anydiff;
+          if (changed) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { x0[j] = prop[j]; u0[j] = un[j]; }
+            last_prior = 0.0;
+            last_like = q_like;
+            ntn_last = (fabs(q_like) <= DBL_MAX) ? q_like : nan_to_num(q_like);
+          }
+          const bool appending = w_append && done + itb == wn - 1;
+          if (own && valid) {
+            *reinterpret_cast<double2 *>(trow_ptr) = make_double2(x0[0], x0[1]);
+            *reinterpret_cast<double2 *>(trow_ptr + 2) = make_double2(x0[2], x0[3]);
+            if (appending) {   // record_history: the last iteration of the launch
+              double *zr = P.st.Z + (size_t)(M + c_global) * ld + i0;
+              *reinterpret_cast<double2 *>(zr) = make_double2(x0[0], x0[1]);
+              *reinterpret_cast<double2 *>(zr + 2) = make_double2(x0[2], x0[3]);
+              for (int pz = 0; pz < P.npeers; ++pz) {   // replicas over NVLink
+                double *zp = P.peer_Z[pz] + (size_t)(M + c_global) * ld + i0;
+                *reinterpret_cast<double2 *>(zp) = make_double2(x0[0], x0[1]);
+                *reinterpret_cast<double2 *>(zp + 2) = make_double2(x0[2], x0[3]);
+              }
+            }
+          }
+          if (appending && (counters || P.publish_k)) {
+            // the row is visible (to the GPU; to the peers when there are any) before the chain counts itself
+            if (P.npeers) __threadfence_system(); else __threadfence();
+            __syncwarp();
+            if (g == 0 && valid) {
+              if (counters) {
+                const uint32_t old = atomicAdd(counters + blk, 1u);
+                if (P.npeers && old == (uint32_t)P.cfg.nchains_local - 1u) {   // this rank's block is complete: tell the peers
+                  __threadfence_system();
+                  for (int pz = 0; pz < P.npeers; ++pz) atomicMax_system(reinterpret_cast<unsigned long long *>(P.peer_flag[pz]), (unsigned long long)(P.ww_k0 + blk + 1));
+                }
+              } else peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
+            }
+          }
+          if (g == 0 && valid) {
+            *lrow_ptr = last_like + last_prior;
+            // decision word (dreamzs_common.cuh pack_decision): snooker, CR index, gamma level, one DE pair, gamma == 1
+            if (drow_ptr)
+              *drow_ptr = (uint32_t)changed | ((mt >> 7) & 2u) | ((mt & 15u) << 2) | (((mt >> 4) & 15u) << 6) | (1u << 10) |
+                          (((mt >> 9) & 1u) << 18) | ((uint32_t)accepted << 19);
+          }
+          trow_ptr += ld; lrow_ptr += 1; if (drow_ptr) drow_ptr += 1;
+          WW_STAMP();   // c: iteration done
+        }
+        // park the chain state for the next batch / the epilogue
+        if (own && valid) {
+          *reinterpret_cast<double2 *>(Xs + cs * ld + i0) = make_double2(x0[0], x0[1]);
+          *reinterpret_cast<double2 *>(Xs + cs * ld + i0 + 2) = make_double2(x0[2], x0[3]);
+          *reinterpret_cast<double2 *>(Us + cs * ld + i0) = make_double2(u0[0], u0[1]);
+          *reinterpret_cast<double2 *>(Us + cs * ld + i0 + 2) = make_double2(u0[2], u0[3]);
+        }
+        if (g == 0 && valid) { cst[cs * 4 + 1] = last_prior; cst[cs * 4 + 2] = last_like; }
+      }
+    }
+    WW_STAMP();   // +5: chains advanced
+    done += nb;
+    __syncthreads();   // the slots are free for the next batch; parked states are visible
+  }
+  if (!resident || last_window) {   // chain states -> global memory
+    for (int i = tid; i < nch_cta * nch; i += WW_THREADS) {
+      const int cs = fdiv20(i, L.m_nch), q = i - cs * nch;
+      const int c_local = cta_chain0 + cs;
+      double2 *xr = reinterpret_cast<double2 *>(P.st.X + (size_t)c_local * ld + 4 * q);
+      const double2 *xs = reinterpret_cast<const double2 *>(Xs + (size_t)cs * ld + 4 * q);
+      xr[0] = xs[0]; xr[1] = xs[1];
+      double2 *ur = reinterpret_cast<double2 *>(P.st.gauss_U + (size_t)c_local * ld + 4 * q);
+      const double2 *us = reinterpret_cast<const double2 *>(Us + (size_t)cs * ld + 4 * q);
+      ur[0] = us[0]; ur[1] = us[1];
+    }
+    if (tid < nch_cta) {
+      P.st.last_prior[cta_chain0 + tid] = cst[tid * 4 + 1];
+      P.st.last_like[cta_chain0 + tid] = cst[tid * 4 + 2];
+    }
+    if (!resident) __syncthreads();   // before the next group's states overwrite the staging area
+  }
+   }   // groups
+   if (w_append) ++blk;
+   wt0 += wn;
+   first_window = false;
+  }   // windows
+#undef WW_STAMP
+}
+
+// ---------------------------------------------------------------- host side
+// u = L^T x for every local chain from the packed factor (dreamzs_init_logp; a window launch may start at any iteration)
+__global__ void __launch_bounds__(128) dreamzs_whiten_kernel(const StepParams P) {
+  const int d = P.cfg.ndim, ld = P.cfg.ld, nK = ld / 4;
+  const int c = blockIdx.x;
+  extern __shared__ double xs_w[];
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) xs_w[j] = P.st.X[(size_t)c * ld + j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+    double acc = 0.0;
+    if (i < d) {
+      const int I = i >> 3;
+      const double *tile0 = P.st.gauss_L + (size_t)wwin_tile0(nK, I) * 32;
+      for (int j = 8 * I; j < d; ++j) {      // L[j][i] lives in tile (I, k = j/4), lane (j%4) + 4 (i%8)
+        const int k = j >> 2;
+        const double lji = tile0[(size_t)(k - 2 * I) * 32 + (j & 3) + 4 * (i & 7)];
+        acc = fma(lji, xs_w[j], acc);
+      }
+    }
+    P.st.gauss_U[(size_t)c * ld + i] = acc;
+  }
+}
+
+struct WwinPlan { int tc, nb, nsplit, isplit[WW_MAXSPLIT + 1], lpc; size_t smem; WwinLayout layout; };
+
+inline int wwin_nsplit(int ncols, int nI) {
+  const int NT = (ncols + 7) / 8;
+  int nsplit = NT > 0 ? WW_WARPS / NT : 0;
+  if (nsplit > WW_MAXSPLIT) nsplit = WW_MAXSPLIT;
+  if (nsplit > nI) nsplit = nI;
+  return nsplit;
+}
+
+// chains per CTA, iterations per batch and the split of the i-tiles; tc == 0: the kernel is not usable for this shape.
+// `tc_force` / `nb_force` > 0 override the choice (experiments).
+inline WwinPlan wwin_plan(const dreamzs_config &cfg, int sms, int niter_max, int tc_force = 0, int nb_force = 0) {
+  WwinPlan pl{};
+  const int ld = cfg.ld, nch = ld / 4, nI = (ld + 7) / 8, nK = ld / 4;
+  if (ld > 128 || (ld & 3) || ld < 8 || cfg.nchains_local < 1) return pl;
+  pl.lpc = nch <= 8 ? 8 : nch <= 16 ? 16 : 32;
+  const int cpw = 32 / pl.lpc;
+  const size_t cap = 227 * 1024;
+  int nb = niter_max < 1 ? 1 : niter_max > 16 ? 16 : niter_max;
+  if (nb_force > 0) nb = nb_force;
+  int tc_want = (cfg.nchains_local + sms - 1) / sms;
+  if (tc_force > 0) tc_want = tc_force;
+  if (tc_want > WW_WARPS * cpw) tc_want = WW_WARPS * cpw;
+  for (;;) {
+    // largest tc <= tc_want that fits shared memory and keeps the product units within the CTA's warps
+    int tc = tc_want, nsplit = 0;
+    for (; tc >= 1; --tc) {
+      nsplit = wwin_nsplit(tc * nb + tc, nI);
+      if (nsplit >= 1 && nsplit * WW_MAXI >= nI && (size_t)wwin_layout(cfg.ndim, ld, tc, nb, cfg.ngamma).bytes <= cap) break;
+    }
+    if (tc >= 1) {
+      // split the i-tiles into nsplit ranges, each of 1..WW_MAXI tiles, minimising the heaviest range (tile I costs
+      // nK - 2 I products): exhaustive over the boundary choices
+      auto wsum = [&](int a, int b) { int w = 0; for (int I = a; I < b; ++I) w += (nK - 2 * I > 0 ? nK - 2 * I : 0); return w; };
+      int best = 1 << 30, cut[WW_MAXSPLIT + 1];
+      cut[0] = 0; cut[nsplit] = nI;
+      for (int c1 = 1; c1 <= nI; ++c1)
+        for (int c2 = c1; c2 <= nI; ++c2)
+          for (int c3 = c2; c3 <= nI; ++c3) {
+            const int cs[3] = {c1, c2, c3};
+            bool pinned = true;                                          // cuts beyond nsplit-1 are pinned to nI
+            for (int q = nsplit - 1; q < 3; ++q) pinned = pinned && cs[q] == nI;
+            if (!pinned) continue;
+            for (int q = 0; q < nsplit - 1; ++q) cut[q + 1] = cs[q];
+            int worst = 0;
+            bool fits = true;
+            for (int q = 0; q < nsplit; ++q) {
+              const int n = cut[q + 1] - cut[q];
+              if (n < 1 || n > WW_MAXI) fits = false;
+              const int w = wsum(cut[q], cut[q + 1]);
+              if (w > worst) worst = w;
+            }
+            if (fits && worst < best) { best = worst; for (int q = 0; q <= nsplit; ++q) pl.isplit[q] = cut[q]; }
+          }
+      if (best < (1 << 30)) {
+        pl.tc = tc; pl.nb = nb; pl.nsplit = nsplit;
+        pl.layout = wwin_layout(cfg.ndim, ld, tc, nb, cfg.ngamma);
+        pl.smem = (size_t)pl.layout.bytes;
+        return pl;
+      }
+    }
+    if (nb == 1 || nb_force > 0) { pl.tc = 0; return pl; }
+    nb = nb > 10 ? 10 : nb > 5 ? 5 : nb - 1;     // fewer iterations per batch
+  }
+}
+
+template <int LPC>
+int launch_wwin_t(StepParams &P, const WwinPlan &pl, int sms, cudaStream_t stream) {
+  auto kern = dreamzs_wwin_kernel<LPC>;
+  static size_t smem_set[64] = {0};
+  if (ensure_dynamic_smem(kern, pl.smem, smem_set) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
+  const int ngroups = (P.cfg.nchains_local + pl.tc - 1) / pl.tc;
+  if (!P.ww_sync) {   // one window: no CTA waits for another, any grid will do
+    kern<<<ngroups, WW_THREADS, pl.smem, stream>>>(P);
+    return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;
+  }
+  // several windows: CTAs wait for rows other CTAs append, so all of them must be resident (cooperative launch); a CTA
+  // walks the chain groups grid-stride
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WW_THREADS, pl.smem) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    return DREAMZS_E_LAUNCH;
+  }
+  const int cap = sms * per_sm;
+  const int grid = ngroups < cap ? ngroups : cap;
+  void *args[] = {(void *)&P};
+  if (cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(WW_THREADS), args, pl.smem, stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return DREAMZS_E_LAUNCH;
+  }
+  return DREAMZS_OK;
+}
+
+}  // namespace dreamzs

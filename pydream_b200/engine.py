@@ -64,6 +64,44 @@ def device_target_table(target, ld):
     return np.ascontiguousarray(target.table(), dtype=np.float64)
 
 
+def whitening_factor(invC):
+    """Lower-triangular L with invC = L L^T (Cholesky of the symmetrised precision matrix in extended precision, rounded
+    to float64), or None when the matrix is not safely positive definite.  The whitened window kernel carries u = L^T x
+    and evaluates x.(invC x) as |u|^2 (include/dreamzs.h dreamzs_state.gauss_L)."""
+    A = np.asarray(invC, dtype=np.longdouble)
+    d = A.shape[0]
+    S = (A + A.T) / 2
+    Lf = np.zeros((d, d), dtype=np.longdouble)
+    for j in range(d):
+        s = S[j, j] - np.dot(Lf[j, :j], Lf[j, :j])
+        if not np.isfinite(s) or s <= 0:
+            return None
+        Lf[j, j] = np.sqrt(s)
+        if j + 1 < d:
+            Lf[j + 1:, j] = (S[j + 1:, j] - Lf[j + 1:, :j] @ Lf[j, :j]) / Lf[j, j]
+    L64 = Lf.astype(np.float64)
+    back = L64.astype(np.longdouble) @ L64.astype(np.longdouble).T
+    scale = float(np.abs(S).max())
+    if not np.all(np.isfinite(L64)) or float(np.abs(back - S).max()) > 1e-13 * scale or float(np.abs(A - A.T).max()) > 1e-10 * scale:
+        return None
+    return L64
+
+
+def pack_whitening(Lw, ld):
+    """L in the tile order of dreamzs_state.gauss_L: for i-tile I and k = 2I .. ld/4-1 a tile of 32 doubles, entry
+    (j % 4) + 4 (i % 8) = L[4k + j%4][8I + i%8]."""
+    d = Lw.shape[0]
+    nK, nI = ld // 4, (ld + 7) // 8
+    P = np.zeros((8 * nI + 8, 8 * nI + 8))
+    P[:d, :d] = Lw
+    tiles = []
+    for I in range(nI):
+        for k in range(2 * I, nK):
+            blk = P[4 * k:4 * k + 4, 8 * I:8 * I + 8]           # [j % 4, i % 8]
+            tiles.append(blk.T.reshape(-1))                     # entry (i % 8) * 4 + (j % 4)
+    return np.concatenate(tiles) if tiles else np.zeros(0)
+
+
 def temperature_ladder(nchains):
     """T[i] = 0.001 ** (i / nchains): the ladder of _sample_dream_pt (pydream/core.py:133-136)."""
     T_ = np.zeros((nchains))
@@ -113,10 +151,11 @@ class DreamEngine:
                  nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
                  history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
                  cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True,
-                 generic_kernel=False, window_kernel=True, reserve_iters=0, peer_archive=True):
+                 generic_kernel=False, window_kernel=True, reserve_iters=0, peer_archive=True, whitened=True, persistent=True):
         if not torch.cuda.is_available():
             raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _cabi.load()
+        self.persistent = bool(persistent)      # one launch for a whole span of windows (whitened window kernel)
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.rank = torch.distributed.get_rank(group) if group is not None else 0
@@ -174,6 +213,17 @@ class DreamEngine:
         dense = target.kind == T.TARGET_GAUSSIAN_DENSE
         self.gauss_Y = torch.zeros((self.Nl, self.ld), **f64) if dense else None
         self.gauss_Q = torch.zeros(self.Nl, **f64) if dense else None
+        # whitened form (dreamzs_state.gauss_L / gauss_U): invC = L L^T, carried u = L^T x
+        self.gauss_L = self.gauss_U = self.sync_ws = None
+        if dense and whitened and self.ld <= 128:
+            Lw = whitening_factor(target.invC)
+            if Lw is not None:
+                packed = pack_whitening(Lw, self.ld)
+                assert packed.size == int(self.lib.dreamzs_whiten_doubles(self.ld))
+                self.gauss_L = torch.from_numpy(packed).to(self.device)
+                self.gauss_U = torch.zeros((self.Nl, self.ld), **f64)
+                # scratch of the persistent multi-window launches (dreamzs_state.sync_ws): abort word + one counter per window
+                self.sync_ws = torch.zeros(16 + 4096, dtype=torch.int32, device=self.device)
         self.cfg = _cabi.Config(abi_version=_cabi.ABI_VERSION, ndim=d, ld=self.ld, nchains_global=N, chain_begin=self.c0,
                                 nchains_local=self.Nl, nCR=nCR, ngamma=gamma_levels, nDEpairs=DEpairs, multitry=multitry,
                                 hardboundaries=int(bool(hardboundaries)), history_thin=self.thin,
@@ -211,7 +261,11 @@ class DreamEngine:
                               prior_kind=p(self.prior_kind), prior_a=p(self.prior_a), prior_b=p(self.prior_b),
                               mins=p(self.mins), maxs=p(self.maxs),
                               gauss_Y=p(self.gauss_Y) if self.gauss_Y is not None else None,
-                              gauss_Q=p(self.gauss_Q) if self.gauss_Q is not None else None)
+                              gauss_Q=p(self.gauss_Q) if self.gauss_Q is not None else None,
+                              gauss_L=p(self.gauss_L) if self.gauss_L is not None else None,
+                              gauss_U=p(self.gauss_U) if self.gauss_U is not None else None,
+                              sync_ws=p(self.sync_ws) if self.sync_ws is not None and self.persistent else None,
+                              sync_ws_words=self.sync_ws.numel() if self.sync_ws is not None and self.persistent else 0)
 
     def _ensure_capacity(self, rows):
         """Make room for `rows` archive rows.  Collective when the archive is shared between ranks."""

@@ -198,3 +198,51 @@ def test_window_kernel_option_space(kw):
     np.testing.assert_array_equal(a[2], b[2])
     assert np.all(np.abs(a[1] - b[1]) <= logp_tol(b[1])), (np.abs(a[1] - b[1]) / logp_tol(b[1])).max()
     np.testing.assert_allclose(a[0], b[0], rtol=1e-10, atol=1e-11)
+
+
+def test_rng_normals_match_contract_bit_for_bit():
+    """The kernels' float32 Box-Muller (csrc/dreamzs_common.cuh normal_pair32) against the numpy statement of the RNG
+    contract (oracle/philox.py): identical bits for 16384 blocks of several (chain, iteration, call) streams."""
+    import ctypes as C
+    import torch
+    from oracle import philox as px
+    from pydream_b200 import _cabi
+    lib = _cabi.load()
+    nb = 16384
+    for seed, chain, it, call in ((0, 0, 0, 0), (0x123456789ABCDEF, 4095, 77, 3), (2 ** 64 - 1, 2 ** 32 - 2, 10 ** 6, 1)):
+        out = torch.empty(4 * nb, dtype=torch.float32, device='cuda')
+        _cabi.check(lib.dreamzs_rng_normals(C.c_uint64(seed), chain, it, call, nb, C.c_void_p(out.data_ptr()), None), 'dreamzs_rng_normals')
+        k0, k1 = px.split_seed(seed)
+        w = px.philox4x32_blocks(nb, (call << 3) | px.ST_NORMAL, it, chain, k0, k1).astype(np.uint32).reshape(nb, 2, 2)
+        n0, n1 = px.normal_pairs32(w[:, :, 0], w[:, :, 1])
+        ref = np.stack([n0, n1], axis=2).reshape(-1)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize('shape', [(50, 333, 41, 10), (100, 150, 57, 25), (24, 700, 33, 10), (128, 40, 26, 4), (9, 900, 21, 1)],
+                         ids=['d50', 'd100_thin25', 'd24', 'd128', 'd9_thin1'])
+def test_whitened_window_kernel_shapes(shape):
+    """The whitened window kernel (DMMA products, flattened draws) over its shape space -- 8 / 16 / 32 lanes per chain,
+    windows longer than a batch, one-iteration windows, chain counts that do not fill the last CTA -- against the C
+    oracle and against the same engine with the kernel switched off (generic path, same draws)."""
+    from oracle import c_oracle
+    from pydream_b200.engine import DreamEngine
+    d, N, T, thin = shape
+    rng = np.random.default_rng(d * 1000 + N)
+    tgt = make_target(dict(kind='gaussian', d=d))
+    hist = rng.uniform(-5, 15, size=(2 * N + 3, d))
+    kw = dict(snooker=.15, history_thin=thin)
+    ref = c_oracle.OracleSampler(d, N, hist, hist[:N], tgt.kind, tgt.table(), seed=8, nthreads=8, **kw).run(T)
+    eng = DreamEngine(d, N, hist, hist[:N], tgt, seed=8, **kw)
+    assert eng.gauss_L is not None
+    states, logp, dec = _run(eng, T)
+    np.testing.assert_array_equal(dec, ref['decisions'])
+    assert np.all(np.abs(logp - ref['logp']) <= logp_tol(ref['logp'])), (np.abs(logp - ref['logp']) / logp_tol(ref['logp'])).max()
+    np.testing.assert_allclose(states, ref['states'], rtol=1e-10, atol=1e-11)
+    gen = _run(DreamEngine(d, N, hist, hist[:N], tgt, seed=8, generic_kernel=True, **kw), T)
+    np.testing.assert_array_equal(dec, gen[2])
+    # any split of the run into launches gives the same trajectory
+    eng2 = DreamEngine(d, N, hist, hist[:N], tgt, seed=8, **kw)
+    parts = [_run(eng2, n) for n in (1, 2, 7, T - 10)]
+    np.testing.assert_array_equal(dec, np.concatenate([p[2] for p in parts], axis=0))
+    np.testing.assert_array_equal(logp, np.concatenate([p[1] for p in parts], axis=0))

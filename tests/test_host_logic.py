@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, 'include', 'dreamzs.h')).read()
-    declared = set(re.findall(r'^(?:int|int64_t)\s+(dreamzs_\w+)\s*\(', hdr, flags=re.M))
+    declared = set(re.findall(r'^(?:int|int64_t|void)\s+(dreamzs_\w+)\s*\(', hdr, flags=re.M))
     assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
     lib = _cabi.load()
     for name in declared:
@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_cabi.Config) == 14 * 4 + 4 * 8 + 8
-    assert C.sizeof(_cabi.State) == 16 * 8
+    assert C.sizeof(_cabi.State) == 20 * 8
     assert C.sizeof(_cabi.Trace) == 5 * 8
     assert C.sizeof(_cabi.Peers) == 8 + 8 * 8 + 8 * 8 + 8 + 8
     assert C.sizeof(_cabi.Adapt) == 8 + 8 + 13 * 8
@@ -252,3 +252,33 @@ def test_dream_option_set_matches_reference(capsys):
         for name in ('mins', 'maxs', 'CR_values', 'gamma_level_values', 'DEpairs', 'gamma_arr', 'CR_probabilities',
                      'gamma_probabilities', 'boundary_mask'):
             np.testing.assert_array_equal(np.asarray(getattr(r, name), dtype=float), np.asarray(getattr(o, name), dtype=float), err_msg=name)
+
+
+def test_whitening_factor_and_packing():
+    """Host side of the whitened window kernel: invC = L L^T to rounding, |L^T x|^2 agrees with x.(invC x) far inside the
+    1e-12 tolerance, the packed tile order is the one include/dreamzs.h documents, a matrix that is not positive
+    definite is refused."""
+    from pydream_b200.engine import whitening_factor, pack_whitening
+    rng = np.random.default_rng(0)
+    for d in (7, 50, 100, 128):
+        tgt = targets.CorrelatedGaussian.benchmark(d)
+        Lw = whitening_factor(tgt.invC)
+        assert Lw is not None and np.allclose(np.triu(Lw, 1), 0)
+        assert np.abs(Lw @ Lw.T - tgt.invC).max() <= 1e-13 * np.abs(tgt.invC).max()
+        for _ in range(20):
+            x = rng.uniform(-5, 15, size=d)
+            q_ref = np.sum(x * np.dot(tgt.invC, x))
+            u = Lw.T @ x
+            assert abs(np.dot(u, u) - q_ref) <= 1e-13 * abs(q_ref)
+        ld = (d + 3) // 4 * 4
+        packed = pack_whitening(Lw, ld)
+        assert packed.size == int(_cabi.load().dreamzs_whiten_doubles(ld))
+        nK = ld // 4
+        tile0 = lambda I: I * nK - I * (I - 1)
+        for (j, i) in ((0, 0), (d - 1, 0), (d - 1, d - 1), (d // 2, d // 3), (5, 6)):
+            I, k = i // 8, j // 4
+            got = packed[(tile0(I) + k - 2 * I) * 32 + (j % 4) + 4 * (i % 8)] if k >= 2 * I else 0.0
+            assert got == (Lw[j, i] if j >= i else 0.0)
+    bad = np.eye(4)
+    bad[3, 3] = -1.0
+    assert whitening_factor(bad) is None

@@ -18,6 +18,21 @@ def main():
     B.build()
     out = os.path.join(ROOT, 'build', 'variants')
     os.makedirs(out, exist_ok=True)
+    if any(x.startswith('-DDZ_WW') for x in defs):      # variants of the whitened window kernel
+        objs = [os.path.join(B.OBJ, f) for f in sorted(os.listdir(B.OBJ)) if f.endswith('.o') and f != 'dreamzs_wwin_inst.o']
+        o = os.path.join(out, '%s_wwin.o' % name)
+        cmd = [B._nvcc()] + B.NVCC_FLAGS + defs + ['-c', os.path.join(B.CSRC, 'dreamzs_wwin_inst.cu'), '-o', o]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise SystemExit(p.stdout + p.stderr)
+        for line in p.stderr.splitlines():
+            if 'spill' in line or 'registers' in line:
+                print(line.strip()[:160])
+        lib = os.path.join(out, 'libdreamzs_%s.so' % name)
+        subprocess.check_call([B._nvcc(), '-shared', '-o', lib] + objs + [o, '-gencode', 'arch=compute_100a,code=sm_100a'])
+        os.remove(o)
+        print(lib)
+        return
     objs = [os.path.join(B.OBJ, f) for f in sorted(os.listdir(B.OBJ)) if f.endswith('.o') and not f.startswith('gwin_')]
     for tc in B.GWIN_VARIANTS:
         o = os.path.join(out, '%s_gwin_%d.o' % (name, tc))

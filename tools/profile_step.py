@@ -13,6 +13,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--generic', action='store_true')
+    ap.add_argument('--old', action='store_true', help='the round-1 window kernel (carried y = invC x) instead of the whitened one')
+    ap.add_argument('--thin', type=int, default=10)
+    ap.add_argument('--nopersist', action='store_true', help='one launch per window instead of one persistent launch per run')
     ap.add_argument('--iters', type=int, default=41)
     ap.add_argument('--chains', type=int, default=1024)
     ap.add_argument('--dim', type=int, default=100)
@@ -37,8 +40,8 @@ def main():
     else:
         tgt = targets.Banana(d)
         hist = rng.normal(size=(a.nseed, d))
-    eng = DreamEngine(d, N, hist, hist[:N], tgt, seed=0, snooker=a.snooker, history_thin=10, multitry=a.multitry,
-                      record_decisions=False, generic_kernel=a.generic)
+    eng = DreamEngine(d, N, hist, hist[:N], tgt, seed=0, snooker=a.snooker, history_thin=a.thin, multitry=a.multitry,
+                      record_decisions=False, generic_kernel=a.generic, whitened=not a.old, persistent=not a.nopersist)
     eng.run(11)
     torch.cuda.synchronize()
     if a.phases:
@@ -54,19 +57,15 @@ def main():
     if a.time:
         ms = e0.elapsed_time(e1)
         print('%s d=%d N=%d: %d iterations in %.3f ms -> %.2f us/iter, %.1f M chain-steps/s, %d launches'
-              % ('generic' if a.generic else 'auto', d, N, a.iters, ms, 1e3 * ms / a.iters, N * a.iters / ms / 1e3,
+              % ('generic' if a.generic else 'old window kernel' if a.old else 'auto', d, N, a.iters, ms, 1e3 * ms / a.iters, N * a.iters / ms / 1e3,
                  eng.launches - l0))
 
 
     if a.phases:
         t = buf.cpu().numpy()
-        n = int((t[:32] != 0).sum())
+        n = int((t != 0).sum())
         print('phase stamps (cycles since kernel entry, CTA 0 thread 0):', [int(v - t[0]) for v in t[1:n]])
         print('deltas:', [int(t[i + 1] - t[i]) for i in range(n - 1)])
-        m = int((t[32:] != 0).sum())
-        if m:   # -DDZ_GW_STAGGER builds also stamp warp 0 of the second warp group
-            g = t[32:32 + m]
-            print('group 1 stamps (same origin):', [int(v - t[0]) for v in g])
 
 
 if __name__ == '__main__':
