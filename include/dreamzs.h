@@ -161,7 +161,7 @@ int dreamzs_rng_normals(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t c
                         void *stream);
 
 /* Profiling aid, not part of the sampler: CTA 0 of the window kernels writes clock64() stamps of its phases into
- * `device_ptr` (>= 64 int64; NULL switches it off).  Process-wide; the only global state of the library. */
+ * `device_ptr` (>= 96 int64; NULL switches it off; entries 60.. accumulate per-phase cycles over all CTAs).  Process-wide; the only global state of the library. */
 void dreamzs_debug_set_phase_buffer(void *device_ptr);
 
 /* Initial log-prior / log-likelihood of the current positions X (first-call branch of

@@ -209,7 +209,7 @@ static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const d
     // only the last iteration of a launch may append (the archive is read-only inside a launch)
     for (int it = 0; it + 1 < niter; ++it)
       if ((iter_begin + it) % cfg->history_thin == 0) return DREAMZS_E_BADARG;
-  } else if (!st->sync_ws || appends_between(iter_begin, niter, cfg->history_thin) + 2 + 16 > st->sync_ws_words) return DREAMZS_E_BADARG;
+  } else if (!st->sync_ws || 2 * (appends_between(iter_begin, niter, cfg->history_thin) + 2) + 16 > st->sync_ws_words) return DREAMZS_E_BADARG;
   if (archive_rows + appends_between(iter_begin, niter, cfg->history_thin) * cfg->nchains_global > st->Z_capacity_rows)
     return DREAMZS_E_BADARG;
   if (niter == 0 || cfg->nchains_local == 0) return DREAMZS_OK;
@@ -218,8 +218,9 @@ static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const d
   P.all_flat = all_flat_hint(cfg);
   if (multi) {
     P.ww_sync = st->sync_ws; P.ww_k0 = k0;
-    // abort word + one counter per appending window of the span, zeroed in stream order
-    const size_t words = 16 + (size_t)appends_between(iter_begin, niter, cfg->history_thin) + 2;
+    P.ww_wcap = (int32_t)appends_between(iter_begin, niter, cfg->history_thin) + 2;
+    // abort word + two counters per appending window of the span (chains appended / forwarded to the peers), zeroed in stream order
+    const size_t words = 16 + 2 * (size_t)P.ww_wcap;
     if (cudaMemsetAsync(st->sync_ws, 0, words * sizeof(uint32_t), (cudaStream_t)stream) != cudaSuccess) { (void)cudaGetLastError(); return DREAMZS_E_LAUNCH; }
   }
   if (temperature) {   // only the generic kernel scales the log-likelihood; the dense-Gaussian kernels assume T = 1
@@ -312,7 +313,7 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
     if (burn) n = 1;
     if (persistent && !burn) {
       // as many whole windows as the scratch words allow
-      const int64_t maxwin = st->sync_ws_words - 32;
+      const int64_t maxwin = (st->sync_ws_words - 32) / 2 - 2;
       int64_t span = end - t;
       if (appends_between(t, span, thin) > maxwin) span = (nxt + (maxwin - 1) * thin + 1) - t;
       const int64_t napp = appends_between(t, span, thin);

@@ -65,14 +65,15 @@ inline WwinLayout wwin_layout(int d, int ld, int TC, int NB, int ngamma) {
   L.oUs = (int32_t)o;    o += up((size_t)TC * ld * 8);
   L.oGam = (int32_t)o;   o += up((size_t)ngamma * d * 8);
   L.oScr = (int32_t)o;   o += up((size_t)9 * L.ncolmax * 8);             // raw scalar draws [kind][column]
-  L.oLogu = (int32_t)o;  o += up((size_t)L.ncolmax * 8);
-  L.oGsn = (int32_t)o;   o += up((size_t)L.ncolmax * 8);
-  L.oRows = (int32_t)o;  o += up((size_t)L.ncolmax * 16);                // snooker z1, z2 row indices
+  L.oLogu = (int32_t)o;  o += up((size_t)2 * L.ncolmax * 8);             // from here: two sets (batch parity)
+  L.oGsn = (int32_t)o;   o += up((size_t)2 * L.ncolmax * 8);
+  L.oRows = (int32_t)o;  o += up((size_t)2 * L.ncolmax * 24);            // row indices: DE r1, r2 | snooker z, z1, z2
+  L.oMeta = (int32_t)o;  o += up((size_t)2 * L.ncolmax * 4);
+  L.oDpr = (int32_t)o;   o += up((size_t)2 * L.ncolmax * 4);
+  L.oMask = (int32_t)o;  o += up((size_t)2 * L.ncolmax * L.nch);
   L.oMbar = (int32_t)o;  o += up((size_t)(L.ncolmax + 1) * 8);
-  L.oMeta = (int32_t)o;  o += up((size_t)L.ncolmax * 4);
-  L.oDpr = (int32_t)o;   o += up((size_t)L.ncolmax * 4);
-  L.oMask = (int32_t)o;  o += up((size_t)L.ncolmax * L.nch);
-  L.oProbs = (int32_t)o; o += 40 * 8;                // [0,16) CR, [16,24) gamma level, 24 snooker, 26 unity, 32 abort flag
+  L.oUses = (int32_t)o;  o += up((size_t)L.ncolmax);                     // TMA uses of a column slot (mbarrier phase)
+  L.oProbs = (int32_t)o; o += 48 * 8;                // [0,16) CR, [16,24) gamma level, 24 snooker, 26 unity, 32 abort flag
   L.oCst = (int32_t)o;   o += up((size_t)TC * 4 * 8);
   // pool of z1 - z2 rows for snooker columns (filled in V2, read by the chains): whatever shared memory is left, at most
   // one slot per column; columns that find the pool full read z1, z2 from the archive inside the chain loop
@@ -109,11 +110,34 @@ __device__ __forceinline__ uint4 philox_inl(uint32_t c0, uint32_t c1, uint32_t c
   return make_uint4(c0, c1, c2, c3);
 }
 
+// Sum over the LPC lanes of a chain on the fp64 MMA path, two DMMAs instead of log2(LPC) shuffle rounds (the chain phase is
+// bound by dependent latency and the fp64 pipe is idle there).  With A = ones, D = A B sums the B fragment's columns:
+// lane l gets the sums of lanes {8m..8m+3} and {8m+4..8m+7}, m = l % 4; their sum T[m] goes through a second product
+// whose A fragment selects the T's of the lane's own chain.  Every lane of a chain ends with the same bits.
+template <int LPC>
+__device__ __forceinline__ double lsum_mma(double v, double a2) {
+  double d0 = 0.0, d1 = 0.0;
+  dmma884(d0, d1, 1.0, v);
+  const double t = d0 + d1;
+  double e0 = 0.0, e1 = 0.0;
+  dmma884(e0, e1, a2, t);
+  return e0;
+}
+// the second product's A fragment: row i = lane / 4 (a lane of chain i * 4 / LPC), column k = lane % 4 (T[k] = lanes 8k..8k+7)
+template <int LPC>
+__device__ __forceinline__ double lsum_mma_sel(int lane) {
+  return ((lane >> 2) * 4) / LPC == ((lane & 3) * 8) / LPC ? 1.0 : 0.0;
+}
+
 template <int LPC>
 __device__ __forceinline__ double lsum(double v) {
 #pragma unroll
   for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) {
@@ -135,13 +159,9 @@ struct RowWait {      // what row_ready needs of the launch parameters (by value
   int32_t *peer_error;
   const uint32_t *counters;
   volatile int32_t *status;
+  long long *dbg;       // profiling aid: [66] cycles spent waiting for rows, [67] waits
 };
-__device__ __noinline__ bool row_wait(const RowWait w, int64_t r) {
-  const int64_t off = r - w.archive_rows;
-  const int j = (int)(off / w.nchains_global);
-  const int owner = (int)(off - (int64_t)j * w.nchains_global);
-  const bool local = owner >= w.chain_begin && owner < w.chain_begin + w.nchains_local;
-  const int q = local ? 0 : owner / w.nchains_local;
+__device__ __noinline__ bool row_wait(const RowWait w, int j, bool local, int q) {
   const uint64_t k = w.k0 + (uint64_t)j + 1u;
   const uint64_t t0 = globaltimer_ns();
   for (;;) {
@@ -155,13 +175,28 @@ __device__ __noinline__ bool row_wait(const RowWait w, int64_t r) {
     __nanosleep(200);
   }
 }
-__device__ __forceinline__ bool row_ready(const RowWait &w, int64_t r) {
-  return (r < w.archive_rows || !w.counters) ? true : row_wait(w, r);
+// `known` (shared memory, zeroed per launch): known[0] = leading append blocks of this launch known complete for the local
+// chains, known[1 + q] = the same for peer q (a writer completes its blocks in order), so that only the first reader of a
+// block pays for the acquire load
+__device__ __forceinline__ bool row_ready(const RowWait &w, int *known, int64_t r) {
+  if (r < w.archive_rows || !w.counters) return true;
+  const int64_t off = r - w.archive_rows;
+  const int j = (int)(off / w.nchains_global);
+  const int owner = (int)(off - (int64_t)j * w.nchains_global);
+  const bool local = owner >= w.chain_begin && owner < w.chain_begin + w.nchains_local;
+  const int q = local ? 0 : owner / w.nchains_local;
+  int *kn = known + (local ? 0 : 1 + q);
+  if (j < *reinterpret_cast<volatile int *>(kn)) return true;
+  const long long t0 = w.dbg ? clock64() : 0;
+  if (!row_wait(w, j, local, q)) return false;
+  if (w.dbg) { atomicAdd(reinterpret_cast<unsigned long long *>(w.dbg) + 66, (unsigned long long)(clock64() - t0)); atomicAdd(reinterpret_cast<unsigned long long *>(w.dbg) + 67, 1ull); }
+  atomicMax(kn, j + 1);
+  return true;
 }
-__device__ __forceinline__ bool rows_ready(const RowWait &w, int64_t ra, int64_t rb, int64_t rc) {
-  bool ok = row_ready(w, ra);
-  ok = row_ready(w, rb) && ok;
-  if (rc >= 0) ok = row_ready(w, rc) && ok;
+__device__ __forceinline__ bool rows_ready(const RowWait &w, int *known, int64_t ra, int64_t rb, int64_t rc) {
+  bool ok = row_ready(w, known, ra);
+  ok = row_ready(w, known, rb) && ok;
+  if (rc >= 0) ok = row_ready(w, known, rc) && ok;
   return ok;
 }
 
@@ -169,27 +204,86 @@ __device__ __forceinline__ bool rows_ready(const RowWait &w, int64_t ra, int64_t
 #define DZ_WW_MINBLOCKS 1
 #endif
 
+// one batch of one window of one group of chains: the unit the kernel's main loop works on
+struct WwItem {
+  int64_t wt0, nxt, M, trace_row0;
+  int wphase, blk, grp, done, seq;
+  int wn, nb, ncol, cta_chain0, nch_cta;
+  bool aligned, first_window, valid, w_append, w_refresh, last_window, do_refresh, first_batch, last_batch;
+};
+__device__ __forceinline__ void ww_derive(WwItem &w, const StepParams &P, int TC, int NB) {
+  const int64_t t_end = P.iter_begin + P.niter;
+  w.valid = w.wt0 < t_end;
+  if (!w.valid) return;
+  w.wn = (int)((t_end < w.nxt + 1 ? t_end : w.nxt + 1) - w.wt0);         // iterations of this window
+  w.w_append = w.wt0 + w.wn - 1 == w.nxt;
+  w.w_refresh = w.wt0 == 0 || (w.aligned && w.wphase == 0);
+  w.last_window = w.wt0 + w.wn >= t_end;
+  w.M = P.archive_rows + (int64_t)w.blk * P.cfg.nchains_global;          // archive rows this window samples
+  w.trace_row0 = P.tr.trace_offset + (w.wt0 - P.iter_begin);
+  w.cta_chain0 = w.grp * TC;
+  w.nch_cta = min(TC, P.cfg.nchains_local - w.cta_chain0);               // chains of this group
+  w.nb = min(NB, w.wn - w.done);
+  w.ncol = w.nch_cta * w.nb;                                             // columns of the batch: col = chain * nb + iteration
+  w.first_batch = w.done == 0;
+  w.last_batch = w.done + w.nb >= w.wn;
+  w.do_refresh = w.w_refresh && w.first_batch;
+}
+__device__ __forceinline__ void ww_first(WwItem &w, const StepParams &P, int TC, int NB) {
+  const int64_t thin = P.cfg.history_thin;
+  w.wt0 = P.iter_begin;
+  w.nxt = ((P.iter_begin + thin - 1) / thin) * thin;          // first appending iteration >= the window's first
+  // a window that starts right after append #a (a = (wt0 - 1) / thin) re-derives u from x when a % REFRESH == 0
+  w.wphase = (int)((P.iter_begin > 0 ? (P.iter_begin - 1) / thin : 0) % DREAMZS_GAUSS_REFRESH_WINDOWS);
+  w.aligned = P.iter_begin == 0 || (P.iter_begin - 1) % thin == 0;
+  w.blk = 0; w.grp = blockIdx.x; w.done = 0; w.seq = 0; w.first_window = true;
+  ww_derive(w, P, TC, NB);
+}
+__device__ __forceinline__ void ww_next(WwItem &w, const StepParams &P, int TC, int NB, int ngroups) {
+  w.seq += 1;
+  w.done += w.nb;
+  if (w.done >= w.wn) {            // next group of the window; after the last one the next window
+    w.done = 0;
+    w.grp += gridDim.x;
+    if (w.grp >= ngroups) {
+      w.grp = blockIdx.x;
+      w.first_window = false;
+      if (w.w_append) {
+        w.blk += 1;
+        if (w.nxt > 0) w.wphase = w.wphase + 1 == DREAMZS_GAUSS_REFRESH_WINDOWS ? 0 : w.wphase + 1;   // the next window follows append #(a + 1)
+        w.nxt += P.cfg.history_thin;
+        w.aligned = true;
+      } else w.aligned = false;
+      w.wt0 += w.wn;
+    }
+  }
+  ww_derive(w, P, TC, NB);
+}
+
 template <int LPC>
 __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kernel(const StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int d = P.cfg.ndim, ld = P.cfg.ld, TC = P.ww_tc, NB = P.ww_nb;
   const WwinLayout &L = P.ww_L;
-  const int nch = L.nch, nK = L.nK;
+  const int nch = L.nch, nK = L.nK, NCM = L.ncolmax;
   double *Lf = reinterpret_cast<double *>(smem_raw + L.oL), *Wc = reinterpret_cast<double *>(smem_raw + L.oW);
   double *Jc = reinterpret_cast<double *>(smem_raw + L.oJ);
   float *Nz = reinterpret_cast<float *>(smem_raw + L.oN);
   double *Xs = reinterpret_cast<double *>(smem_raw + L.oXs), *Us = reinterpret_cast<double *>(smem_raw + L.oUs);
   double *gam = reinterpret_cast<double *>(smem_raw + L.oGam);
   uint2 *scr = reinterpret_cast<uint2 *>(smem_raw + L.oScr);
-  double *logu = reinterpret_cast<double *>(smem_raw + L.oLogu), *gsn = reinterpret_cast<double *>(smem_raw + L.oGsn);
-  int64_t *rows = reinterpret_cast<int64_t *>(smem_raw + L.oRows);
+  // two sets of the per-column scalars (batch parity): the draws of the NEXT batch are made while the chains run this one
+  double *logu2 = reinterpret_cast<double *>(smem_raw + L.oLogu), *gsn2 = reinterpret_cast<double *>(smem_raw + L.oGsn);
+  int64_t *rows2 = reinterpret_cast<int64_t *>(smem_raw + L.oRows);
+  uint32_t *meta2 = reinterpret_cast<uint32_t *>(smem_raw + L.oMeta);
+  int *dpr2 = reinterpret_cast<int *>(smem_raw + L.oDpr);
+  unsigned char *mask2 = smem_raw + L.oMask;
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + L.oMbar);   // [0, ncolmax) columns, [ncolmax] the factor
-  uint32_t *meta = reinterpret_cast<uint32_t *>(smem_raw + L.oMeta);
-  int *dpr = reinterpret_cast<int *>(smem_raw + L.oDpr);
-  unsigned char *maskb = smem_raw + L.oMask;
+  unsigned char *uses = smem_raw + L.oUses;                            // TMA uses of a column slot so far (mbarrier phase)
   double *probs = reinterpret_cast<double *>(smem_raw + L.oProbs), *cst = reinterpret_cast<double *>(smem_raw + L.oCst);
   double *pool = reinterpret_cast<double *>(smem_raw + L.oPool);
   int *pool_n = reinterpret_cast<int *>(probs + 34);          // snooker columns of the batch that hold a pool slot
+  int *known = reinterpret_cast<int *>(probs + 35);           // [1 + DREAMZS_MAX_PEERS] append blocks known complete (row_ready)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double logF = P.st.target_table[0];
   int dbg_n = 0;
@@ -203,10 +297,14 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
   const bool resident = ngroups <= (int)gridDim.x;                  // one group per CTA: chain states stay in shared memory
   volatile int32_t *status = reinterpret_cast<volatile int32_t *>(P.ww_sync);     // word 0: != 0 aborts the launch
   uint32_t *counters = P.ww_sync ? P.ww_sync + 16 : nullptr;                     // chains that have made append #j of this launch
+  constexpr int CPW = 32 / LPC;                                     // chains per warp in the chain phase
+  const int NCW = (TC + CPW - 1) / CPW;                             // warps [0, NCW) run the chains
+  const int n_pre = (WW_WARPS - NCW) * 32;                          // threads that draw the next batch meanwhile
+  const bool overlap = n_pre >= 64;                                 // (too few left: the draws follow the chains instead)
 
   // ---- prologue: one TMA bulk copy brings the packed factor; tables -> shared memory
-  if (tid <= L.ncolmax) mbar_init(mbar + tid, 1);
-  if (tid < 40) {
+  if (tid <= NCM) mbar_init(mbar + tid, 1);
+  if (tid < 48) {
     double v = 0.0;
     if (tid < 16) v = tid < P.cfg.nCR ? P.st.cr_probs[tid] : 0.0;
     else if (tid < 24) v = tid - 16 < P.cfg.ngamma ? P.st.gamma_probs[tid - 16] : 0.0;
@@ -214,7 +312,7 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
     else if (tid == 26) v = P.cfg.p_gamma_unity;
     probs[tid] = v;
   }
-  for (int i = tid; i < L.ncolmax; i += WW_THREADS) meta[i] = 0;      // bit 11 carries a column slot's mbarrier phase
+  for (int i = tid; i < NCM; i += WW_THREADS) uses[i] = 0;
   for (int i = tid; i < P.cfg.ngamma * d; i += WW_THREADS) {   // gamma_table[level][0][:] (one DE pair)
     const int lv = i / d;
     gam[i] = P.st.gamma_table[(size_t)lv * P.cfg.nDEpairs * d + (i - lv * d)];
@@ -232,64 +330,36 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
   if (tid == 0) {
     fence_proxy_async();
     const uint32_t bytes = (uint32_t)L.ntilesL * 256u;
-    mbar_expect_tx(mbar + L.ncolmax, bytes);
-    tma_load_row(Lf, P.st.gauss_L, bytes, mbar + L.ncolmax);
+    mbar_expect_tx(mbar + NCM, bytes);
+    tma_load_row(Lf, P.st.gauss_L, bytes, mbar + NCM);
   }
   WW_STAMP();   // 1: prologue done
   bool factor_ready = false;
+  long long tprev = (P.dbg && tid == 0) ? clock64() : 0;
+  const RowWait rw = {P.archive_rows, P.cfg.nchains_global, P.cfg.chain_begin, P.cfg.nchains_local, P.ww_k0, P.my_flags,
+                      P.peer_error, counters, status, P.dbg};
 
-  // ================================================================ windows of the launch (pydream/core.py:103-122)
-  // A window ends at an appending iteration (t % history_thin == 0); the archive it samples is the one of the launch's
-  // start plus the appends of the windows before it.  CTAs do not synchronise per window: a column whose sampled row was
-  // appended during THIS launch waits for the chains that write that block (counters / peer flags), nothing else waits.
-  const int64_t t_end = P.iter_begin + P.niter;
-  const int64_t thin = P.cfg.history_thin;
-  int blk = 0;                                    // appends made by the windows before the current one (this launch)
-  bool first_window = true;
-  for (int64_t wt0 = P.iter_begin; wt0 < t_end;) {
-   const int64_t nxt = ((wt0 + thin - 1) / thin) * thin;            // first appending iteration >= wt0
-   const int wn = (int)((t_end < nxt + 1 ? t_end : nxt + 1) - wt0); // iterations of this window
-   const bool w_append = (wt0 + wn - 1) % thin == 0;
-   const bool w_refresh = wt0 == 0 || ((wt0 - 1) % thin == 0 && ((wt0 - 1) / thin) % DREAMZS_GAUSS_REFRESH_WINDOWS == 0);
-   const bool last_window = wt0 + wn >= t_end;
-   const int64_t M = P.archive_rows + (int64_t)blk * P.cfg.nchains_global;   // archive rows this window samples
-   const int64_t trace_row0 = P.tr.trace_offset + (wt0 - P.iter_begin);
-   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-  const int cta_chain0 = grp * TC;
-  const int nch_cta = min(TC, P.cfg.nchains_local - cta_chain0);   // chains of this group
-  if (!resident || first_window) {   // chain states -> shared memory
-    for (int i = tid; i < nch_cta * nch; i += WW_THREADS) {
-      const int cs = fdiv20(i, L.m_nch), q = i - cs * nch;
-      const int c_local = cta_chain0 + cs;
-      const double2 *xr = reinterpret_cast<const double2 *>(P.st.X + (size_t)c_local * ld + 4 * q);
-      double2 *xd = reinterpret_cast<double2 *>(Xs + (size_t)cs * ld + 4 * q);
-      xd[0] = xr[0]; xd[1] = xr[1];
-      if (!w_refresh) {
-        const double2 *ur = reinterpret_cast<const double2 *>(P.st.gauss_U + (size_t)c_local * ld + 4 * q);
-        double2 *ud = reinterpret_cast<double2 *>(Us + (size_t)cs * ld + 4 * q);
-        ud[0] = ur[0]; ud[1] = ur[1];
-      }
-    }
-    if (tid < nch_cta) {
-      cst[tid * 4 + 1] = P.st.last_prior[cta_chain0 + tid];
-      cst[tid * 4 + 2] = P.st.last_like[cta_chain0 + tid];
-    }
-    __syncthreads();
-  }
-
-  int done = 0;
-  for (int batch = 0; done < wn; ++batch) {
-    const int nb = min(NB, wn - done);
-    const int ncol = nch_cta * nb;                 // columns of this batch: col = chain * nb + iteration
+  // ================================================================ pre(batch): everything of a batch that needs neither
+  // the column slots nor the chain state -- scalar draws, decisions, archive row indices (waiting for rows appended inside
+  // this launch), crossover masks and d' -- by the threads [ptid of pn], synchronised on named barrier `bar`
+  auto pre = [&](const WwItem &w, int ptid, int pn, int bar) {
+    const int set = w.seq & 1;
+    double *logu = logu2 + set * NCM, *gsn = gsn2 + set * NCM;
+    int64_t *rows = rows2 + (size_t)set * NCM * 3;
+    uint32_t *meta = meta2 + set * NCM;
+    int *dpr = dpr2 + set * NCM;
+    unsigned char *maskb = mask2 + (size_t)set * NCM * nch;
+    const int ncol = w.ncol, nb = w.nb;
     const uint32_t m_nb = fdiv20_magic(nb), m_nch = L.m_nch;
-    const bool do_refresh = w_refresh && batch == 0;
-    // ================================================================ S: scalar draws (thread per (kind, column))
-    for (int task = tid; task < 9 * ncol; task += WW_THREADS) {
+    // ---- S: scalar draws (thread per (kind, column)), one Philox block each:
+    //      0-3: snooker, CR, gamma level, gamma unity (Dream.py:542-599, 615); 4-5: the first two np.random.uniform()
+    //      (snooker gamma :618 / Metropolis :993); 6-8: random.sample calls 0-2 (sample_from_history, :646-668)
+    for (int task = ptid; task < 9 * ncol; task += pn) {
       int kind = 0, col = task;
       while (col >= ncol) { col -= ncol; ++kind; }
       const int ch = fdiv20(col, m_nb), itb = col - ch * nb;
-      const uint32_t iter = (uint32_t)(wt0 + done + itb);
-      const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
+      const uint32_t iter = (uint32_t)(w.wt0 + w.done + itb);
+      const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + w.cta_chain0 + ch);
       uint32_t call = 0, st = ST_MULTINOMIAL;
       const double *pp = probs + 24;
       int n = 2;
@@ -299,10 +369,10 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
       else if (kind == 4) { st = ST_UNIFORM_SCAL; }
       else if (kind == 5) { call = 1; st = ST_UNIFORM_SCAL; }
       else if (kind >= 6) { call = (uint32_t)(kind - 6); st = ST_SAMPLE; }
-      const uint4 w = philox_inl(0u, (call << 3) | st, iter, c_global, k0, k1);
-      uint2 out = make_uint2(w.x, w.y);
+      const uint4 wd = philox_inl(0u, (call << 3) | st, iter, c_global, k0, k1);
+      uint2 out = make_uint2(wd.x, wd.y);
       if (kind < 4) {          // np.random.multinomial(1, p): inverse CDF on a running sum
-        const double u = u53_of(w.x, w.y);
+        const double u = u53_of(wd.x, wd.y);
         double acc = 0.0;
         int idx = n - 1;
         bool found = false;
@@ -313,84 +383,132 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
         out.x = (uint32_t)idx;
       }
       if (kind == 4 || kind == 5) {   // both candidates for the Metropolis uniform: log u now, off the per-column path
-        const double lg = log(u53_of(w.x, w.y));
+        const double lg = log(u53_of(wd.x, wd.y));
         if (kind == 5) out = make_uint2((uint32_t)__double2loint(lg), (uint32_t)__double2hiint(lg));
-        else reinterpret_cast<double *>(logu)[col] = lg;
+        else logu[col] = lg;
       }
-      scr[kind * L.ncolmax + col] = out;
+      scr[kind * NCM + col] = out;
     }
-    if (tid == 0) *pool_n = 0;
-    __syncthreads();
-    // ---- one thread per column: decisions, log u, archive rows -> TMA
-    const RowWait rw = {P.archive_rows, P.cfg.nchains_global, P.cfg.chain_begin, P.cfg.nchains_local, P.ww_k0, P.my_flags,
-                        P.peer_error, counters, status};
-    for (int col = tid; col < ncol; col += WW_THREADS) {
-      const uint2 q0 = scr[col], q1 = scr[L.ncolmax + col], q2 = scr[2 * L.ncolmax + col], q3 = scr[3 * L.ncolmax + col];
-      const uint2 u4 = scr[4 * L.ncolmax + col], u5 = scr[5 * L.ncolmax + col];
-      const uint2 r6 = scr[6 * L.ncolmax + col], r7 = scr[7 * L.ncolmax + col], r8 = scr[8 * L.ncolmax + col];
+    if (ptid == 0) *pool_n = 0;
+    named_sync(bar, pn);
+    // ---- one thread per column: decisions, archive rows
+    for (int col = ptid; col < ncol; col += pn) {
+      const uint2 q0 = scr[col], q1 = scr[NCM + col], q2 = scr[2 * NCM + col], q3 = scr[3 * NCM + col];
+      const uint2 u4 = scr[4 * NCM + col], u5 = scr[5 * NCM + col];
+      const uint2 r6 = scr[6 * NCM + col], r7 = scr[7 * NCM + col], r8 = scr[8 * NCM + col];
       const bool snk = (s0 != 0u) && q0.x == 0u;
-      // meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set in V2), 10 "not unity"
-      const uint32_t ph = meta[col] & 2048u;                 // mbarrier phase this use of the slot completes (bit 11)
-      uint32_t mt = q1.x | (q2.x << 4) | (snk ? 256u : 0u) | (q3.x != 0u ? 1024u : 0u) | (ph ^ 2048u);
+      const uint32_t use = uses[col];
+      uses[col] = (unsigned char)(use + 1u);
+      // meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set in V2), 10 "not unity",
+      // 11 parity of the mbarrier phase this use of the column slot completes
+      uint32_t mt = q1.x | (q2.x << 4) | (snk ? 256u : 0u) | (q3.x != 0u ? 1024u : 0u) | ((use & 1u) << 11);
       // Metropolis uniform: the 2nd np.random.uniform() after a snooker gamma, else the 1st (its log is in place)
       if (snk) logu[col] = __hiloint2double((int)u5.y, (int)u5.x);
-      double *js = Jc + (size_t)col * ld, *ws = Wc + (size_t)col * ld;
-      mbar_expect_tx(mbar + col, 2u * row_bytes);
+      bool ok;
       if (!snk) {
-        const int64_t ra = (int64_t)(((uint64_t)r6.x * (uint64_t)M) >> 32);
-        int64_t rb = (int64_t)(((uint64_t)r6.y * (uint64_t)(M - 1)) >> 32);
+        const int64_t ra = (int64_t)(((uint64_t)r6.x * (uint64_t)w.M) >> 32);
+        int64_t rb = (int64_t)(((uint64_t)r6.y * (uint64_t)(w.M - 1)) >> 32);
         if (rb >= ra) rb += 1;
-        if (!rows_ready(rw, ra, rb, -1)) probs[32] = 1.0;
-        fence_proxy_async();   // the slots' earlier generic-proxy accesses and the acquired rows are ordered before the async copies
-        tma_load_row(js, P.st.Z + (size_t)ra * ld, row_bytes, mbar + col);   // z_r1 -> J slot
-        tma_load_row(ws, P.st.Z + (size_t)rb * ld, row_bytes, mbar + col);   // z_r2 -> W slot
+        rows[3 * col] = ra; rows[3 * col + 1] = rb;
+        ok = rows_ready(rw, known, ra, rb, -1);
+        dpr[col] = 0;
+        gsn[col] = ((double)(q1.x + 1u) / (double)P.cfg.nCR) * 4294967296.0;   // DE column: CR 2^32 for the crossover test
       } else {
         const double g = 1.2 + (2.2 - 1.2) * u53_of(u4.x, u4.y);             // snooker gamma, Dream.py:618
         gsn[col] = g;
         if (g == 1.0) mt |= 512u;
-        const int64_t rz = (int64_t)(((uint64_t)r6.x * (uint64_t)M) >> 32);
-        rows[2 * col] = (int64_t)(((uint64_t)r7.x * (uint64_t)M) >> 32);
-        rows[2 * col + 1] = (int64_t)(((uint64_t)r8.x * (uint64_t)M) >> 32);
+        const int64_t rz = (int64_t)(((uint64_t)r6.x * (uint64_t)w.M) >> 32);
+        const int64_t r1 = (int64_t)(((uint64_t)r7.x * (uint64_t)w.M) >> 32), r2 = (int64_t)(((uint64_t)r8.x * (uint64_t)w.M) >> 32);
+        rows[3 * col] = rz; rows[3 * col + 1] = r1; rows[3 * col + 2] = r2;
+        ok = rows_ready(rw, known, rz, r1, r2);
         const int slot = atomicAdd(pool_n, 1);                               // z1 - z2 goes to the pool when a slot is left
         dpr[col] = slot < L.npool ? slot : -1;
-        if (!rows_ready(rw, rz, rows[2 * col], rows[2 * col + 1])) probs[32] = 1.0;
-        fence_proxy_async();
-        tma_load_row(js, P.st.Z + (size_t)rz * ld, row_bytes, mbar + col);   // z -> J slot and W slot (-> L^T z)
-        tma_load_row(ws, P.st.Z + (size_t)rz * ld, row_bytes, mbar + col);
       }
+      if (!ok) probs[32] = 1.0;
       meta[col] = mt;
-      if (!snk) dpr[col] = 0;
     }
-    __syncthreads();
-    WW_STAMP();   // +0: rows requested
-    // ================================================================ V1: crossover uniforms -> keep mask, d'
+    named_sync(bar, pn);
+    // ---- V1: crossover uniforms -> keep mask, d'
     const int ntask = ncol * nch;
-    for (int task = tid; task < ntask; task += WW_THREADS) {
+    for (int task = ptid; task < ntask; task += pn) {
       const int col = fdiv20(task, m_nch), q = task - col * nch;
       const uint32_t mt = meta[col];
       if (mt & 256u) continue;
       const int ch = fdiv20(col, m_nb), itb = col - ch * nb;
-      const uint32_t iter = (uint32_t)(wt0 + done + itb);
-      const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + cta_chain0 + ch);
+      const uint32_t iter = (uint32_t)(w.wt0 + w.done + itb);
+      const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + w.cta_chain0 + ch);
       const uint4 wu = philox_inl((uint32_t)q, (1u << 3) | ST_UNIFORM_VEC, iter, c_global, k0, k1);
       // U = w 2^-32 exactly, so U < CR <=> w < ceil(CR 2^32) and U > CR <=> w > floor(CR 2^32)
-      const double CRs = ((double)((mt & 15u) + 1u) / (double)P.cfg.nCR) * 4294967296.0;
+      const double CRs = gsn[col];
       const uint64_t t_lt = (uint64_t)ceil(CRs), t_gt = (uint64_t)floor(CRs);
+      const bool lt_all = (t_lt >> 32) != 0, gt_none = (t_gt >> 32) != 0;   // CR = 1: every U < CR, none > CR
+      const uint32_t tl = (uint32_t)t_lt, tg = (uint32_t)t_gt;
       const uint32_t wv[4] = {wu.x, wu.y, wu.z, wu.w};
       unsigned reset = 0;
       int cnt = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (4 * q + j < d) {
-          cnt += ((uint64_t)wv[j] < t_lt);
-          if ((uint64_t)wv[j] > t_gt) reset |= 1u << j;
+          cnt += (lt_all || wv[j] < tl);
+          if (!gt_none && wv[j] > tg) reset |= 1u << j;
         } else reset |= 1u << j;
       }
       maskb[task] = (unsigned char)reset;
       if (cnt) atomicAdd(dpr + col, cnt);
     }
-    __syncthreads();
-    WW_STAMP();   // +1: masks
+  };
+
+  // ================================================================ batches of the launch (pydream/core.py:103-122)
+  // A window ends at an appending iteration (t % history_thin == 0); the archive it samples is the one of the launch's
+  // start plus the appends of the windows before it.  CTAs do not synchronise per window: a column whose sampled row was
+  // appended during THIS launch waits for the chains that write that block (counters / peer flags), nothing else waits.
+  WwItem it;
+  ww_first(it, P, TC, NB);
+  if (it.valid) pre(it, tid, WW_THREADS, 1);
+  __syncthreads();
+  while (it.valid) {
+    if (probs[32] != 0.0) return;   // a wait for appended rows timed out (or another CTA aborted): give up, the host raises
+    const int set = it.seq & 1;
+    double *logu = logu2 + set * NCM, *gsn = gsn2 + set * NCM;
+    int64_t *rows = rows2 + (size_t)set * NCM * 3;
+    uint32_t *meta = meta2 + set * NCM;
+    int *dpr = dpr2 + set * NCM;
+    unsigned char *maskb = mask2 + (size_t)set * NCM * nch;
+    const int64_t wt0 = it.wt0, M = it.M, trace_row0 = it.trace_row0;
+    const int done = it.done, nb = it.nb, ncol = it.ncol, wn = it.wn, blk = it.blk;
+    const int cta_chain0 = it.cta_chain0, nch_cta = it.nch_cta;
+    const bool w_append = it.w_append, do_refresh = it.do_refresh;
+    const uint32_t m_nb = fdiv20_magic(nb), m_nch = L.m_nch;
+    const int ntask = ncol * nch;
+    if (it.first_batch && (!resident || it.first_window)) {   // chain states -> shared memory
+      for (int i = tid; i < nch_cta * nch; i += WW_THREADS) {
+        const int cs = fdiv20(i, L.m_nch), q = i - cs * nch;
+        const int c_local = cta_chain0 + cs;
+        const double2 *xr = reinterpret_cast<const double2 *>(P.st.X + (size_t)c_local * ld + 4 * q);
+        double2 *xd = reinterpret_cast<double2 *>(Xs + (size_t)cs * ld + 4 * q);
+        xd[0] = xr[0]; xd[1] = xr[1];
+        if (!it.w_refresh) {
+          const double2 *ur = reinterpret_cast<const double2 *>(P.st.gauss_U + (size_t)c_local * ld + 4 * q);
+          double2 *ud = reinterpret_cast<double2 *>(Us + (size_t)cs * ld + 4 * q);
+          ud[0] = ur[0]; ud[1] = ur[1];
+        }
+      }
+      if (tid < nch_cta) {
+        cst[tid * 4 + 1] = P.st.last_prior[cta_chain0 + tid];
+        cst[tid * 4 + 2] = P.st.last_like[cta_chain0 + tid];
+      }
+    }
+    // ---- the archive rows of the batch's columns, staged by TMA straight into the column slots:
+    //      DE: z_r1 -> J slot, z_r2 -> W slot;   snooker: z -> J slot and W slot (-> L^T z)
+    for (int col = tid; col < ncol; col += WW_THREADS) {
+      fence_proxy_async();   // the slots' earlier generic-proxy accesses and the acquired rows are ordered before the async copies
+      mbar_expect_tx(mbar + col, 2u * row_bytes);
+      const int64_t ra = rows[3 * col], rb = (meta[col] & 256u) ? ra : rows[3 * col + 1];
+      tma_load_row(Jc + (size_t)col * ld, P.st.Z + (size_t)ra * ld, row_bytes, mbar + col);
+      tma_load_row(Wc + (size_t)col * ld, P.st.Z + (size_t)rb * ld, row_bytes, mbar + col);
+    }
+    WW_STAMP();   // +0: rows requested
+    const long long tp0 = (P.dbg && tid == 0) ? clock64() : 0;
     // ================================================================ V2: zeta, e, gamma -> J, dx in place of the rows
     for (int task = tid; task < ntask; task += WW_THREADS) {
       const int col = fdiv20(task, m_nch), q = task - col * nch;
@@ -398,14 +516,14 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
       if (mt & 256u) {   // snooker column: z1 - z2 (Dream.py:810) -> pool slot; z / L^T z arrive by TMA
         const int slot = dpr[col];
         if (slot >= 0) {
-          const double *z1 = P.st.Z + (size_t)rows[2 * col] * ld + 4 * q, *z2 = P.st.Z + (size_t)rows[2 * col + 1] * ld + 4 * q;
+          const double *z1 = P.st.Z + (size_t)rows[3 * col + 1] * ld + 4 * q, *z2 = P.st.Z + (size_t)rows[3 * col + 2] * ld + 4 * q;
           const double2 p01 = __ldg(reinterpret_cast<const double2 *>(z1)), p23 = __ldg(reinterpret_cast<const double2 *>(z1) + 1);
           const double2 q01 = __ldg(reinterpret_cast<const double2 *>(z2)), q23 = __ldg(reinterpret_cast<const double2 *>(z2) + 1);
           double2 *bs = reinterpret_cast<double2 *>(pool + (size_t)slot * ld + 4 * q);
           bs[0] = make_double2(p01.x - q01.x, p01.y - q01.y);
           bs[1] = make_double2(p23.x - q23.x, p23.y - q23.y);
         }
-        mbar_wait(mbar + col, ((mt >> 11) & 1u) ^ 1u);
+        mbar_wait(mbar + col, (mt >> 11) & 1u);
         continue;
       }
       const int ch = fdiv20(col, m_nb), itb = col - ch * nb;
@@ -424,7 +542,7 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
       if (q == 0 && gamma == 1.0) atomicOr(meta + col, 512u);
       double *js = Jc + (size_t)col * ld + 4 * q, *ws = Wc + (size_t)col * ld + 4 * q;
       float *ns = Nz + (size_t)col * ld + 4 * q;
-      mbar_wait(mbar + col, ((mt >> 11) & 1u) ^ 1u);
+      mbar_wait(mbar + col, (mt >> 11) & 1u);
       const double2 a01 = *reinterpret_cast<const double2 *>(js), a23 = *reinterpret_cast<const double2 *>(js + 2);
       const double2 b01 = *reinterpret_cast<const double2 *>(ws), b23 = *reinterpret_cast<const double2 *>(ws + 2);
       const double diff[4] = {a01.x - b01.x, a01.y - b01.y, a23.x - b23.x, a23.y - b23.y};
@@ -451,10 +569,10 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
         wd[0] = xs[0]; wd[1] = xs[1];
       }
     }
-    if (!factor_ready) { mbar_wait(mbar + L.ncolmax, 0); factor_ready = true; }   // the factor has landed
+    if (!factor_ready) { mbar_wait(mbar + NCM, 0); factor_ready = true; }   // the factor has landed
     __syncthreads();
-    if (probs[32] != 0.0) return;   // a wait for appended rows timed out (or another CTA aborted): give up, the host raises
-    WW_STAMP();   // +2: columns generated
+    WW_STAMP();   // +1: columns generated
+    const long long tp1 = (P.dbg && tid == 0) ? clock64() : 0;
     // ================================================================ M: DU = DX^T L on DMMA
     // unit = (8-column tile, range of i-tiles) -> one warp (the host picks TC, NB and the split so that units <= 32 and a
     // range holds <= WW_MAXI i-tiles).  D fragment: lane l holds du[column l/4][8 I + 2 (l%4) + {0,1}].
@@ -480,14 +598,15 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
             const int ka = 2 * I0, kb = two ? min(2 * I1, nK) : nK;   // k in [ka, kb) feeds I0 only, [kb, nK) feeds both
             const double *b0 = Lf + (size_t)wwin_tile0(nK, I0) * 32 + lane;
             const double *b1 = Lf + (size_t)wwin_tile0(nK, two ? I1 : I0) * 32 + lane;
-#pragma unroll 1
-            for (int k = ka; k < kb; ++k) dmma884(acc[t][0], acc[t][1], arow[4 * k], b0[(size_t)(k - ka) * 32]);
-            if (two) {
+            const double *ap = arow + 4 * ka;
 #pragma unroll 2
-              for (int k = kb; k < nK; ++k) {
-                const double a = arow[4 * k];
-                dmma884(acc[t][0], acc[t][1], a, b0[(size_t)(k - ka) * 32]);
-                dmma884(acc[t + 1][0], acc[t + 1][1], a, b1[(size_t)(k - kb) * 32]);
+            for (int k = ka; k < kb; ++k, ap += 4, b0 += 32) dmma884(acc[t][0], acc[t][1], *ap, *b0);
+            if (two) {
+#pragma unroll 4
+              for (int k = kb; k < nK; ++k, ap += 4, b0 += 32, b1 += 32) {
+                const double a = *ap;
+                dmma884(acc[t][0], acc[t][1], a, *b0);
+                dmma884(acc[t + 1][0], acc[t + 1][1], a, *b1);
               }
             }
           }
@@ -509,7 +628,15 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
       __syncthreads();
     }
     WW_STAMP();   // +4: products written
-    // ================================================================ C: the chains (LPC lanes per chain)
+    WW_STAMP();   // +4: products written
+    const long long tp2 = (P.dbg && tid == 0) ? clock64() : 0;
+    // ================================================================ the chains run this batch on warps [0, NCW) while the
+    // other warps make the draws of the next one
+    WwItem nx = it;
+    ww_next(nx, P, TC, NB, ngroups);
+    if (warp >= NCW) {
+      if (nx.valid && overlap) pre(nx, tid - NCW * 32, n_pre, 2);
+    } else
     {
       constexpr int CPW = 32 / LPC;                     // chains per warp
       const int sub = lane / LPC, g = lane - sub * LPC;
@@ -533,6 +660,7 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
         }
         double ntn_last = nan_to_num(1.0 * last_like + last_prior);
         const double zeta = P.cfg.zeta;
+        const double a2sel = lsum_mma_sel<LPC>(lane);
         double *trow_ptr = P.tr.trace + ((size_t)c_local * P.tr.trace_iters + (trace_row0 + done)) * ld + i0;
         double *lrow_ptr = P.tr.trace_logp + (size_t)c_local * P.tr.trace_iters + (trace_row0 + done);
         uint32_t *drow_ptr = P.tr.decisions ? P.tr.decisions + (size_t)c_local * P.tr.trace_iters + (trace_row0 + done) : nullptr;
@@ -556,6 +684,7 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
             prop[3] = (x0[3] + j23.y) + zeta * (double)nn.w;
             un[0] = u0[0] + w01.x; un[1] = u0[1] + w01.y; un[2] = u0[2] + w23.x; un[3] = u0[3] + w23.y;
           }
+          double part = 0.0;
           if (__any_sync(0xffffffffu, run_snooker)) {
             // snooker_update, Dream.py:827-835 (single-point form); J slot = z, W slot = L^T z, z1 - z2 read from the archive
             double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
@@ -568,7 +697,7 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
                 const double2 b23 = *reinterpret_cast<const double2 *>(pool + (size_t)slot * ld + i0 + 2);
                 b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
               } else {              // pool full: read the two rows here
-                const double *z1 = P.st.Z + (size_t)rows[2 * col] * ld + i0, *z2 = P.st.Z + (size_t)rows[2 * col + 1] * ld + i0;
+                const double *z1 = P.st.Z + (size_t)rows[3 * col + 1] * ld + i0, *z2 = P.st.Z + (size_t)rows[3 * col + 2] * ld + i0;
                 const double2 p01 = __ldg(reinterpret_cast<const double2 *>(z1)), p23 = __ldg(reinterpret_cast<const double2 *>(z1) + 1);
                 const double2 q01 = __ldg(reinterpret_cast<const double2 *>(z2)), q23 = __ldg(reinterpret_cast<const double2 *>(z2) + 1);
                 b[0] = p01.x - q01.x; b[1] = p01.y - q01.y; b[2] = p23.x - q23.x; b[3] = p23.y - q23.y;
@@ -583,10 +712,14 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
               D = fma(v[j], v[j], D);
               b[j] = b[j] * v[j];
             }
-            D = lsum<LPC>(D);
+            // |q0 - z|^2 and (z1 - z2).(q0 - z) in ONE pass of shuffles; the projection coefficient is then their quotient
+            // (Dream.py:829-831 divides element-wise and sums: same value up to the rounding of the summation order;
+            // 0 where D == 0, as the masked divide leaves it)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) S += (D != 0) ? b[j] / D : 0.0;
-            const double sc = nan_to_num(lsum<LPC>(S));
+            for (int j = 0; j < 4; ++j) S += b[j];
+            D = lsum_mma<LPC>(D, a2sel);
+            S = lsum_mma<LPC>(S, a2sel);
+            const double sc = (D != 0) ? nan_to_num(S / D) : 0.0;
             const double cg = gamma * sc;
             double nn = 0.0;
 #pragma unroll
@@ -597,27 +730,32 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
               nn = fma(ww, ww, nn);
               if (run_snooker) prop[j] = o;
             }
-            nn = lsum<LPC>(nn);
+            if (run_snooker && own) {   // L^T dx = c (u - L^T z)
+              const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
+              un[0] = u0[0] + cg * (u0[0] - w01.x); un[1] = u0[1] + cg * (u0[1] - w01.y);
+              un[2] = u0[2] + cg * (u0[2] - w23.x); un[3] = u0[3] + cg * (u0[3] - w23.y);
+            }
+            part = fma(un[1], un[1], un[0] * un[0]) + fma(un[3], un[3], un[2] * un[2]);
+            // |prop - z|^2 and Q' together
+            nn = lsum_mma<LPC>(nn, a2sel);
+            part = lsum_mma<LPC>(part, a2sel);
             if (run_snooker) {
-              if (own) {   // L^T dx = c (u - L^T z)
-                const double2 w01 = *reinterpret_cast<const double2 *>(ws), w23 = *reinterpret_cast<const double2 *>(ws + 2);
-                un[0] = u0[0] + cg * (u0[0] - w01.x); un[1] = u0[1] + cg * (u0[1] - w01.y);
-                un[2] = u0[2] + cg * (u0[2] - w23.x); un[3] = u0[3] + cg * (u0[3] - w23.y);
-              }
               const double norm = sqrt(nn);
               snk_logp = (norm != 0 ? log(norm) : 0.0) * (d - 1);
               const double n0 = sqrt(D);
               cur = (n0 != 0 ? log(n0) : 0.0) * (d - 1);
             }
+          } else {
+            part = fma(un[1], un[1], un[0] * un[0]) + fma(un[3], un[3], un[2] * un[2]);
+            part = lsum_mma<LPC>(part, a2sel);
           }
-          double part = fma(un[1], un[1], un[0] * un[0]) + fma(un[3], un[3], un[2] * un[2]);
+          const double Qn = part;
           int anydiff = (prop[0] != x0[0]) | (prop[1] != x0[1]) | (prop[2] != x0[2]) | (prop[3] != x0[3]);
           if (LPC == 32) anydiff = __any_sync(0xffffffffu, anydiff);
           else {
             const unsigned bal = __ballot_sync(0xffffffffu, anydiff);
             anydiff = ((bal >> (sub * LPC)) & ((LPC == 32) ? 0xffffffffu : ((1u << LPC) - 1u))) != 0u;
           }
-          const double Qn = lsum<LPC>(part);
           const double q_like = logF - .5 * Qn;
           // mr = nan_to_num(q_logp) - nan_to_num(last_logp) (Dream.py:334); nan_to_num is the identity on finite values,
           // which one comparison establishes (|x| <= DBL_MAX is false for inf and nan)
@@ -641,25 +779,22 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
               double *zr = P.st.Z + (size_t)(M + c_global) * ld + i0;
               *reinterpret_cast<double2 *>(zr) = make_double2(x0[0], x0[1]);
               *reinterpret_cast<double2 *>(zr + 2) = make_double2(x0[2], x0[3]);
-              for (int pz = 0; pz < P.npeers; ++pz) {   // replicas over NVLink
-                double *zp = P.peer_Z[pz] + (size_t)(M + c_global) * ld + i0;
-                *reinterpret_cast<double2 *>(zp) = make_double2(x0[0], x0[1]);
-                *reinterpret_cast<double2 *>(zp + 2) = make_double2(x0[2], x0[3]);
-              }
+              if (!counters)   // one launch per window: replicas over NVLink from here (multi-window launches: pushed by one warp below)
+                for (int pz = 0; pz < P.npeers; ++pz) {
+                  double *zp = P.peer_Z[pz] + (size_t)(M + c_global) * ld + i0;
+                  *reinterpret_cast<double2 *>(zp) = make_double2(x0[0], x0[1]);
+                  *reinterpret_cast<double2 *>(zp + 2) = make_double2(x0[2], x0[3]);
+                }
             }
           }
           if (appending && (counters || P.publish_k)) {
-            // the row is visible (to the GPU; to the peers when there are any) before the chain counts itself
-            if (P.npeers) __threadfence_system(); else __threadfence();
+            // the row is visible before the chain counts itself: to this GPU (multi-window launch: local readers watch the
+            // counter), to the peers as well when the chain's warp stores the replicas itself
+            if (!counters && P.npeers) __threadfence_system(); else __threadfence();
             __syncwarp();
             if (g == 0 && valid) {
-              if (counters) {
-                const uint32_t old = atomicAdd(counters + blk, 1u);
-                if (P.npeers && old == (uint32_t)P.cfg.nchains_local - 1u) {   // this rank's block is complete: tell the peers
-                  __threadfence_system();
-                  for (int pz = 0; pz < P.npeers; ++pz) atomicMax_system(reinterpret_cast<unsigned long long *>(P.peer_flag[pz]), (unsigned long long)(P.ww_k0 + blk + 1));
-                }
-              } else peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
+              if (counters) atomicAdd(counters + blk, 1u);
+              else peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
             }
           }
           if (g == 0 && valid) {
@@ -683,31 +818,68 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
       }
     }
     WW_STAMP();   // +5: chains advanced
-    done += nb;
-    __syncthreads();   // the slots are free for the next batch; parked states are visible
-  }
-  if (!resident || last_window) {   // chain states -> global memory
-    for (int i = tid; i < nch_cta * nch; i += WW_THREADS) {
-      const int cs = fdiv20(i, L.m_nch), q = i - cs * nch;
-      const int c_local = cta_chain0 + cs;
-      double2 *xr = reinterpret_cast<double2 *>(P.st.X + (size_t)c_local * ld + 4 * q);
-      const double2 *xs = reinterpret_cast<const double2 *>(Xs + (size_t)cs * ld + 4 * q);
-      xr[0] = xs[0]; xr[1] = xs[1];
-      double2 *ur = reinterpret_cast<double2 *>(P.st.gauss_U + (size_t)c_local * ld + 4 * q);
-      const double2 *us = reinterpret_cast<const double2 *>(Us + (size_t)cs * ld + 4 * q);
-      ur[0] = us[0]; ur[1] = us[1];
+    const long long tp3 = (P.dbg && tid == 0) ? clock64() : 0;
+    __syncthreads();   // the slots are free for the next batch; parked states and the next batch's draws are visible
+    if (P.dbg && tid == 0) {   // profiling aid: cycles of every CTA's batches by phase, summed over the grid
+      unsigned long long *acc = reinterpret_cast<unsigned long long *>(P.dbg) + 60;
+      const long long tp4 = clock64();
+      atomicAdd(acc + 0, 1ull);                                  // batches
+      atomicAdd(acc + 1, (unsigned long long)(tp1 - tp0));       // columns (V2)
+      atomicAdd(acc + 2, (unsigned long long)(tp2 - tp1));       // products (M)
+      atomicAdd(acc + 3, (unsigned long long)(tp3 - tp2));       // chains of warp 0 (C)
+      atomicAdd(acc + 4, (unsigned long long)(tp4 - tp3));       // waiting for the other warps (slower chains / the next batch's draws)
+      atomicAdd(acc + 5, (unsigned long long)(tp0 - tprev));     // loop top -> rows requested (TMA issue, states)
+      tprev = tp4;
     }
-    if (tid < nch_cta) {
-      P.st.last_prior[cta_chain0 + tid] = cst[tid * 4 + 1];
-      P.st.last_like[cta_chain0 + tid] = cst[tid * 4 + 2];
+    if (!overlap && nx.valid) {
+      pre(nx, tid, WW_THREADS, 1);
+      __syncthreads();
     }
-    if (!resident) __syncthreads();   // before the next group's states overwrite the staging area
+    if (counters && P.npeers && w_append && it.last_batch && warp == WW_WARPS - 1) {
+      // Multi-window launch on several GPUs: ONE warp forwards the group's appended rows to the peers' replicas (the rows
+      // are in this GPU's archive and visible to the CTA after the barrier), fences once at system scope, counts the
+      // group and -- when this rank's block is complete -- publishes append #(k0 + blk + 1).  The other warps are already
+      // on the next batch; the system-scope fence is off every chain's path.
+      const int i0p = 4 * lane;
+      if (i0p < ld)
+        for (int cs = 0; cs < nch_cta; ++cs) {
+          const size_t row = (size_t)(M + P.cfg.chain_begin + cta_chain0 + cs) * ld + i0p;
+          const double2 a = *reinterpret_cast<const double2 *>(P.st.Z + row), b = *reinterpret_cast<const double2 *>(P.st.Z + row + 2);
+          for (int pz = 0; pz < P.npeers; ++pz) {
+            *reinterpret_cast<double2 *>(P.peer_Z[pz] + row) = a;
+            *reinterpret_cast<double2 *>(P.peer_Z[pz] + row + 2) = b;
+          }
+        }
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t old = atomicAdd(counters + P.ww_wcap + blk, (uint32_t)nch_cta);
+        if (old + (uint32_t)nch_cta == (uint32_t)P.cfg.nchains_local) {
+          __threadfence_system();
+          for (int pz = 0; pz < P.npeers; ++pz)
+            atomicMax_system(reinterpret_cast<unsigned long long *>(P.peer_flag[pz]), (unsigned long long)(P.ww_k0 + blk + 1));
+        }
+      }
+    }
+    if (it.last_batch && (!resident || it.last_window)) {   // chain states -> global memory
+      for (int i = tid; i < nch_cta * nch; i += WW_THREADS) {
+        const int cs = fdiv20(i, L.m_nch), q = i - cs * nch;
+        const int c_local = cta_chain0 + cs;
+        double2 *xr = reinterpret_cast<double2 *>(P.st.X + (size_t)c_local * ld + 4 * q);
+        const double2 *xs = reinterpret_cast<const double2 *>(Xs + (size_t)cs * ld + 4 * q);
+        xr[0] = xs[0]; xr[1] = xs[1];
+        double2 *ur = reinterpret_cast<double2 *>(P.st.gauss_U + (size_t)c_local * ld + 4 * q);
+        const double2 *us = reinterpret_cast<const double2 *>(Us + (size_t)cs * ld + 4 * q);
+        ur[0] = us[0]; ur[1] = us[1];
+      }
+      if (tid < nch_cta) {
+        P.st.last_prior[cta_chain0 + tid] = cst[tid * 4 + 1];
+        P.st.last_like[cta_chain0 + tid] = cst[tid * 4 + 2];
+      }
+      if (!resident) __syncthreads();   // before the next group's states overwrite the staging area
+    }
+    it = nx;
   }
-   }   // groups
-   if (w_append) ++blk;
-   wt0 += wn;
-   first_window = false;
-  }   // windows
 #undef WW_STAMP
 }
 
@@ -811,8 +983,9 @@ int launch_wwin_t(StepParams &P, const WwinPlan &pl, int sms, cudaStream_t strea
     kern<<<ngroups, WW_THREADS, pl.smem, stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;
   }
-  // several windows: CTAs wait for rows other CTAs append, so all of them must be resident (cooperative launch); a CTA
-  // walks the chain groups grid-stride
+  // several windows: CTAs wait for rows other CTAs append, so all of them must be resident: at most one wave, a CTA
+  // walks the chain groups grid-stride.  A plain launch (a cooperative one would not overlap the copies that drain the
+  // previous chunk of samples): should other work hold SMs, the missing CTAs start when it ends; waits time out, not hang.
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WW_THREADS, pl.smem) != cudaSuccess || per_sm < 1) {
     (void)cudaGetLastError();
@@ -820,12 +993,8 @@ int launch_wwin_t(StepParams &P, const WwinPlan &pl, int sms, cudaStream_t strea
   }
   const int cap = sms * per_sm;
   const int grid = ngroups < cap ? ngroups : cap;
-  void *args[] = {(void *)&P};
-  if (cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(WW_THREADS), args, pl.smem, stream) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return DREAMZS_E_LAUNCH;
-  }
-  return DREAMZS_OK;
+  kern<<<grid, WW_THREADS, pl.smem, stream>>>(P);
+  return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;
 }
 
 }  // namespace dreamzs

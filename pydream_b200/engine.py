@@ -19,6 +19,7 @@ NCCL after every appending launch instead.
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -155,7 +156,8 @@ class DreamEngine:
         if not torch.cuda.is_available():
             raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _cabi.load()
-        self.persistent = bool(persistent)      # one launch for a whole span of windows (whitened window kernel)
+        # one launch for a whole span of windows (whitened window kernel); DREAMZS_NOPERSIST=1: one launch per window (A/B)
+        self.persistent = bool(persistent) and not os.environ.get('DREAMZS_NOPERSIST')
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.rank = torch.distributed.get_rank(group) if group is not None else 0
@@ -216,9 +218,12 @@ class DreamEngine:
         # whitened form (dreamzs_state.gauss_L / gauss_U): invC = L L^T, carried u = L^T x
         self.gauss_L = self.gauss_U = self.sync_ws = None
         if dense and whitened and self.ld <= 128:
-            Lw = whitening_factor(target.invC)
-            if Lw is not None:
-                packed = pack_whitening(Lw, self.ld)
+            cache = target.__dict__.setdefault('_whitening_cache', {})     # the factor depends on the target only
+            if self.ld not in cache:
+                Lw = whitening_factor(target.invC)
+                cache[self.ld] = None if Lw is None else pack_whitening(Lw, self.ld)
+            packed = cache[self.ld]
+            if packed is not None:
                 assert packed.size == int(self.lib.dreamzs_whiten_doubles(self.ld))
                 self.gauss_L = torch.from_numpy(packed).to(self.device)
                 self.gauss_U = torch.zeros((self.Nl, self.ld), **f64)

@@ -46,7 +46,7 @@ def main():
     torch.cuda.synchronize()
     if a.phases:
         import ctypes
-        buf = torch.zeros(64, dtype=torch.int64, device='cuda')
+        buf = torch.zeros(96, dtype=torch.int64, device='cuda')
         eng.lib.dreamzs_debug_set_phase_buffer(ctypes.c_void_p(buf.data_ptr()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.launches
@@ -63,9 +63,18 @@ def main():
 
     if a.phases:
         t = buf.cpu().numpy()
-        n = int((t != 0).sum())
-        print('phase stamps (cycles since kernel entry, CTA 0 thread 0):', [int(v - t[0]) for v in t[1:n]])
-        print('deltas:', [int(t[i + 1] - t[i]) for i in range(n - 1)])
+        acc = t[60:70].copy()
+        t = t[:60]
+        if acc[0]:
+            nb = float(acc[0])
+            print('all CTAs, cycles per batch: columns %.0f, products %.0f, chains (warp 0) %.0f, wait for other warps %.0f, loop top %.0f; '
+                  'row waits: %d, %.0f cycles each' % (acc[1] / nb, acc[2] / nb, acc[3] / nb, acc[4] / nb, acc[5] / nb, acc[7], acc[6] / max(acc[7], 1)))
+        t0 = int(t[t != 0].min()) if (t != 0).any() else 0
+        for name, lo in (('C warp 0 (iteration ends)', 0), ('V warps (fill start, fill end, next pre end)', 20), ('M', 40)):
+            seg = [int(v - t0) for v in t[lo:lo + 20] if v != 0]
+            if seg:
+                print('%s: %s' % (name, seg))
+                print('   deltas: %s' % [seg[i + 1] - seg[i] for i in range(len(seg) - 1)])
 
 
 if __name__ == '__main__':
