@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DREAMZS_ABI_VERSION 3
+#define DREAMZS_ABI_VERSION 4
 
 /* status codes */
 #define DREAMZS_OK 0
@@ -132,6 +132,13 @@ typedef struct dreamzs_state {
    * launch.  Without it every window is its own launch. */
   uint32_t *sync_ws;
   int64_t sync_ws_words;
+  /* Optional (may be NULL): scratch of the two-stage multi-try step (multitry > 1, ld <= 32, multitry <= 8 / (ld > 16 ? 2 : 1)):
+   * dreamzs_draw_ws_bytes(cfg, iterations per launch) bytes, 16-byte aligned.  With it a launch is two kernels: one makes
+   * every draw of the window (decisions, archive gathers, e, zeta, crossover masks) for all (chain, iteration, point)
+   * in parallel and leaves them here, the other walks the chains (proposal assembly, log-density, selection,
+   * acceptance).  Without it the fused multi-try kernel does both per chain. */
+  double *draw_ws;
+  int64_t draw_ws_bytes;
 } dreamzs_state;
 
 /* Per-launch outputs (device pointers; any may be NULL except trace/trace_logp). */
@@ -153,6 +160,10 @@ int dreamzs_abi_version(void);
 
 /* Length (doubles) of the packed whitening factor dreamzs_state.gauss_L for row stride ld. */
 int64_t dreamzs_whiten_doubles(int32_t ld);
+
+/* Bytes of dreamzs_state.draw_ws for launches of up to `niter` iterations (0: the two-stage multi-try step does not apply
+ * to this configuration). */
+int64_t dreamzs_draw_ws_bytes(const dreamzs_config *cfg, int32_t niter);
 
 /* RNG contract, normal variates (stream 2; DESIGN.md "RNG contract"): the 4 * nblocks float32 normals of call
  * `call_no` of chain `chain` at iteration `iter` under `seed`, written to out (device, float32).  Lets a test pin the

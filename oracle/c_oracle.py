@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 MAX_NCR, MAX_NGAMMA = 16, 8
-ABI_VERSION = 3     # DREAMZS_ABI_VERSION of include/dreamzs.h (checked by dreamzs_oracle_run)
+ABI_VERSION = 4     # DREAMZS_ABI_VERSION of include/dreamzs.h (checked by dreamzs_oracle_run)
 
 
 class Config(C.Structure):
@@ -26,7 +26,8 @@ class State(C.Structure):
                 ('gamma_table', C.c_void_p), ('target_table', C.c_void_p), ('prior_kind', C.c_void_p),
                 ('prior_a', C.c_void_p), ('prior_b', C.c_void_p), ('mins', C.c_void_p), ('maxs', C.c_void_p),
                 ('gauss_Y', C.c_void_p), ('gauss_Q', C.c_void_p), ('gauss_L', C.c_void_p), ('gauss_U', C.c_void_p),
-                ('sync_ws', C.c_void_p), ('sync_ws_words', C.c_int64)]     # unused by the oracle (NULL)
+                ('sync_ws', C.c_void_p), ('sync_ws_words', C.c_int64),
+                ('draw_ws', C.c_void_p), ('draw_ws_bytes', C.c_int64)]     # the last four: unused by the oracle (NULL)
 
 
 class Adapt(C.Structure):

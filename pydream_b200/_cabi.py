@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DREAMZS_LIB') or os.path.join(HERE, 'libdreamzs.so')   # DREAMZS_LIB: A/B testing of builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, E_BADARG, E_LAUNCH, E_UNSUPPORTED = 0, -1, -2, -3
 MAX_NCR, MAX_NGAMMA, MAX_DEPAIRS, MAX_MULTITRY, MAX_NDIM = 16, 8, 8, 16, 1024
 FLAG_ALL_FLAT = 1
@@ -24,7 +24,7 @@ EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_
            'dreamzs_shared_alloc', 'dreamzs_shared_open', 'dreamzs_shared_close', 'dreamzs_shared_free', 'dreamzs_adapt_workspace_bytes',
            'dreamzs_adapt_colsum', 'dreamzs_adapt_colsq', 'dreamzs_adapt_jumps', 'dreamzs_adapt_finish',
            'dreamzs_gr_chain_stats', 'dreamzs_gr_finish', 'dreamzs_whiten_doubles', 'dreamzs_rng_normals',
-           'dreamzs_debug_set_phase_buffer']
+           'dreamzs_debug_set_phase_buffer', 'dreamzs_draw_ws_bytes']
 
 
 class Config(C.Structure):
@@ -41,7 +41,8 @@ class State(C.Structure):
                 ('gamma_table', C.c_void_p), ('target_table', C.c_void_p), ('prior_kind', C.c_void_p),
                 ('prior_a', C.c_void_p), ('prior_b', C.c_void_p), ('mins', C.c_void_p), ('maxs', C.c_void_p),
                 ('gauss_Y', C.c_void_p), ('gauss_Q', C.c_void_p), ('gauss_L', C.c_void_p), ('gauss_U', C.c_void_p),
-                ('sync_ws', C.c_void_p), ('sync_ws_words', C.c_int64)]
+                ('sync_ws', C.c_void_p), ('sync_ws_words', C.c_int64),
+                ('draw_ws', C.c_void_p), ('draw_ws_bytes', C.c_int64)]
 
 
 class Trace(C.Structure):
@@ -113,6 +114,7 @@ def load():
         'dreamzs_whiten_doubles': (i64, [i32]),
         'dreamzs_rng_normals': (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, i32, vp, vp]),
         'dreamzs_debug_set_phase_buffer': (None, [vp]),
+        'dreamzs_draw_ws_bytes': (i64, [cfgp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

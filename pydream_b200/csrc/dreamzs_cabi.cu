@@ -9,6 +9,8 @@ using namespace dreamzs;
 #define DZ_DECL(g, r) int dreamzs_launch_step_##g##_##r(const dreamzs::StepParams &, int, size_t, cudaStream_t);
 DZ_DECL(4, 1) DZ_DECL(8, 1) DZ_DECL(16, 1) DZ_DECL(32, 1) DZ_DECL(32, 2) DZ_DECL(32, 4) DZ_DECL(32, 8)
 #undef DZ_DECL
+int dreamzs_launch_mtp_4(const dreamzs::StepParams &, size_t, cudaStream_t);
+int dreamzs_launch_mtp_8(const dreamzs::StepParams &, size_t, cudaStream_t);
 int dreamzs_launch_gauss_7(const dreamzs::StepParams &, cudaStream_t);
 int dreamzs_launch_gauss_8(const dreamzs::StepParams &, cudaStream_t);
 size_t dreamzs_launch_gauss_smem_bytes(const dreamzs_config &cfg, int TC);
@@ -79,6 +81,22 @@ static bool gwin_eligible(const StepParams &P) {
          !(cfg.flags & DREAMZS_FLAG_NO_WINDOW_KERNEL) && dreamzs_gwin_usable(cfg, 8);
 }
 
+// multi-try with k points side by side in a warp: lane-groups of 4 (ld <= 16) or 8 (ld <= 32) lanes per point
+static bool mtp_eligible(const StepParams &P) {
+  const dreamzs_config &cfg = P.cfg;
+  const int chunks = cfg.ld / 4, G = chunks <= 4 ? 4 : 8;
+  return cfg.multitry > 1 && !P.ext_phase && !P.init_only && chunks <= 8 && cfg.multitry <= 32 / G &&
+         !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL);
+}
+
+extern "C" int64_t dreamzs_draw_ws_bytes(const dreamzs_config *cfg, int32_t niter) {
+  if (!cfg || niter < 1) return 0;
+  StepParams P{};
+  P.cfg = *cfg;
+  if (!mtp_eligible(P)) return 0;
+  return (int64_t)cfg->nchains_local * niter * (8 + (2 * cfg->multitry - 1) * 2 * cfg->ld) * (int64_t)sizeof(double);
+}
+
 static int dispatch(StepParams &P, cudaStream_t stream) {
   const dreamzs_config &cfg = P.cfg;
   const int chunks = cfg.ld / 4;
@@ -111,6 +129,18 @@ static int dispatch(StepParams &P, cudaStream_t stream) {
   int G = 32, R = 1;
   if (chunks <= 4) G = 4; else if (chunks <= 8) G = 8; else if (chunks <= 16) G = 16;
   else { R = (chunks + 31) / 32; if (R > 2 && R <= 4) R = 4; else if (R > 4) R = 8; }
+  // multi-try iteration with the points of a batch side by side, a warp per chain (dreamzs_mtp_kernel.cuh): two kernels
+  // (draws of the window, then the chains) when the caller gave scratch for the draws, else fused
+  if (mtp_eligible(P)) {
+    const int PP = 32 / G;
+    const size_t chain_b = (size_t)(threads / 32) * ((size_t)PP * cfg.ld + 3 * DREAMZS_MAX_MULTITRY) * sizeof(double);
+    const size_t table_b = (size_t)((P.table_doubles + 1) & ~1) * sizeof(double);
+    P.table_in_smem = (table_b + chain_b <= 200 * 1024) ? 1 : 0;
+    P.nslots = PP;
+    if (P.st.draw_ws && (P.st.draw_ws_bytes < dreamzs_draw_ws_bytes(&cfg, P.niter))) P.st.draw_ws = nullptr;
+    const size_t smem_b = chain_b + (P.table_in_smem ? table_b : 0);
+    return G == 4 ? dreamzs_launch_mtp_4(P, smem_b, stream) : dreamzs_launch_mtp_8(P, smem_b, stream);
+  }
   const int chains_per_cta = (threads / 32) * (32 / G);
   const size_t chain_bytes = (size_t)chains_per_cta * ((size_t)P.nslots * cfg.ld + 3 * DREAMZS_MAX_MULTITRY) * sizeof(double);
   const size_t table_bytes = (size_t)((P.table_doubles + 1) & ~1) * sizeof(double);

@@ -199,12 +199,13 @@ __device__ __forceinline__ const double2 *row_ptr(const double *Z, int64_t row, 
   return reinterpret_cast<const double2 *>(Z + (size_t)row * ld + i0);
 }
 
-// One DE proposal, generate_proposal_points DE branch (pydream/Dream.py:688-726) with
-// sample_from_history (:646-668) and set_gamma (:601-626).  p = point index in a batch of n.
+// The state-independent part of one DE proposal, generate_proposal_points DE branch (pydream/Dream.py:688-726) with
+// sample_from_history (:646-668) and set_gamma (:601-626): the jump J = (e*gamma)*(sum z_r1 - sum z_r2), zeta and the
+// crossover mask (bit 4r+j: the dimension keeps the centre value).  p = point index in a batch of n.
 template <int G, int R>
-__device__ __forceinline__ void de_point(const Ctx<G, R> &c, Stream &s, const Decisions &dc, const Bases &b, int n,
-                                         int p, int64_t M, const double (&ctr)[R][4], double (&out)[R][4],
-                                         bool &gamma_one) {
+__device__ __forceinline__ void de_draw(const Ctx<G, R> &c, Stream &s, const Decisions &dc, const Bases &b, int n,
+                                        int p, int64_t M, double (&J)[R][4], double (&zeta)[R][4], unsigned &reset,
+                                        bool &gamma_one) {
   const StepParams &P = c.P;
   const int d = c.d, delta = dc.delta;
   const double *Z = P.st.Z;
@@ -254,8 +255,8 @@ __device__ __forceinline__ void de_point(const Ctx<G, R> &c, Stream &s, const De
     }
   }
   // --- per-dimension variates: zeta (normal), e (uniform), U (uniform); d' = #{U < CR}
-  double zeta[R][4], e[R][4];
-  unsigned reset = 0;  // bit 4r+j: U > CR  -> dimension keeps the centre value
+  double e[R][4];
+  reset = 0;  // bit 4r+j: U > CR  -> dimension keeps the centre value
   int dprime = 0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -295,20 +296,32 @@ __device__ __forceinline__ void de_point(const Ctx<G, R> &c, Stream &s, const De
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
+    for (int j = 0; j < 4; ++j) J[r][j] = (e[r][j] * gamma) * diff[r][j];
+}
+
+// One DE proposal around `ctr` (Dream.py:717-726)
+template <int G, int R>
+__device__ __forceinline__ void de_point(const Ctx<G, R> &c, Stream &s, const Decisions &dc, const Bases &b, int n,
+                                         int p, int64_t M, const double (&ctr)[R][4], double (&out)[R][4],
+                                         bool &gamma_one) {
+  double J[R][4], zeta[R][4];
+  unsigned reset;
+  de_draw<G, R>(c, s, dc, b, n, p, M, J, zeta, reset, gamma_one);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = c.dim0(r) + j;
-      double v = ctr[r][j] + (e[r][j] * gamma) * diff[r][j] + zeta[r][j];
+      double v = ctr[r][j] + J[r][j] + zeta[r][j];
       if ((reset >> (4 * r + j)) & 1u) v = ctr[r][j];
-      out[r][j] = (i < d) ? v : 0.0;
+      out[r][j] = (i < c.d) ? v : 0.0;
     }
 }
 
-// One snooker proposal, snooker_update (pydream/Dream.py:798-837); gamma was drawn once per batch.
-// Returns snooker_logp of the point and D = |ctr - z|^2.
+// The archive rows of one snooker proposal (Dream.py:802-810): z (the projection anchor) and z1 - z2.
 template <int G, int R>
-__device__ __forceinline__ void snooker_point(const Ctx<G, R> &c, Stream &s, const Bases &b, int n, int p, int64_t M,
-                                              double gamma, const double (&ctr)[R][4], double (&out)[R][4],
-                                              double &snk_logp, double &Dout) {
+__device__ __forceinline__ void snooker_rows(const Ctx<G, R> &c, const Stream &s, const Bases &b, int n, int p, int64_t M,
+                                             double (&z)[R][4], double (&t)[R][4]) {
   const StepParams &P = c.P;
   const int d = c.d;
   const double *Z = P.st.Z;
@@ -318,8 +331,6 @@ __device__ __forceinline__ void snooker_point(const Ctx<G, R> &c, Stream &s, con
   const int64_t rz = (int64_t)(((uint64_t)wz.x * (uint64_t)M) >> 32);
   const int64_t r1 = (int64_t)(((uint64_t)w1.x * (uint64_t)M) >> 32);
   const int64_t r2 = (int64_t)(((uint64_t)w2.x * (uint64_t)M) >> 32);
-  double v[R][4], z[R][4], t[R][4];
-  double D = 0.0, S = 0.0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int i0 = c.dim0(r);
@@ -333,6 +344,21 @@ __device__ __forceinline__ void snooker_point(const Ctx<G, R> &c, Stream &s, con
 #pragma unroll
       for (int j = 0; j < 4; ++j) { z[r][j] = 0.0; t[r][j] = 0.0; }
     }
+  }
+}
+
+// snooker_update (pydream/Dream.py:811-837) given the rows: the proposal, snooker_logp of the point and D = |ctr - z|^2
+// (t = z1 - z2 is overwritten).
+template <int G, int R>
+__device__ __forceinline__ void snooker_compute(const Ctx<G, R> &c, int n, double gamma, const double (&ctr)[R][4],
+                                                const double (&z)[R][4], double (&t)[R][4], double (&out)[R][4],
+                                                double &snk_logp, double &Dout) {
+  const int d = c.d;
+  double v[R][4];
+  double D = 0.0, S = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i0 = c.dim0(r);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool ok = i0 + j < d;
@@ -371,6 +397,17 @@ __device__ __forceinline__ void snooker_point(const Ctx<G, R> &c, Stream &s, con
   const double norm = sqrt(gsum<G>(nn, c.gmask));
   snk_logp = (norm != 0 ? log(norm) : 0.0) * (d - 1);   // log(where=False) pinned to 0
   Dout = D;
+}
+
+// One snooker proposal, snooker_update (pydream/Dream.py:798-837); gamma was drawn once per batch.
+// Returns snooker_logp of the point and D = |ctr - z|^2.
+template <int G, int R>
+__device__ __forceinline__ void snooker_point(const Ctx<G, R> &c, Stream &s, const Bases &b, int n, int p, int64_t M,
+                                              double gamma, const double (&ctr)[R][4], double (&out)[R][4],
+                                              double &snk_logp, double &Dout) {
+  double z[R][4], t[R][4];
+  snooker_rows<G, R>(c, s, b, n, p, M, z, t);
+  snooker_compute<G, R>(c, n, gamma, ctr, z, t, out, snk_logp, Dout);
 }
 
 // The call numbers a batch of n points consumes (the bookkeeping at the end of gen_eval_batch), without the rand()

@@ -152,7 +152,7 @@ class DreamEngine:
                  nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
                  history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
                  cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True,
-                 generic_kernel=False, window_kernel=True, reserve_iters=0, peer_archive=True, whitened=True, persistent=True):
+                 generic_kernel=False, window_kernel=True, reserve_iters=0, peer_archive=True, whitened=True, persistent=True, two_stage=True):
         if not torch.cuda.is_available():
             raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _cabi.load()
@@ -235,6 +235,9 @@ class DreamEngine:
                                 target_kind=int(target.kind), flags=(_cabi.FLAG_ALL_FLAT if self.all_flat else 0) | (_cabi.FLAG_GENERIC_KERNEL if generic_kernel else 0)
                                 | (0 if window_kernel else _cabi.FLAG_NO_WINDOW_KERNEL),
                                 snooker=snooker, p_gamma_unity=p_gamma_unity, lamb=lamb, zeta=zeta, seed=int(seed) & (2 ** 64 - 1))
+        # scratch of the two-stage multi-try step (dreamzs_state.draw_ws): every draw of a window, made ahead of the chains
+        nb = int(self.lib.dreamzs_draw_ws_bytes(C.byref(self.cfg), self.thin)) if (two_stage and not self.external) else 0
+        self.draw_ws = torch.empty(nb // 8, **f64) if 0 < nb <= 2 ** 31 else None
         ws = self.lib.dreamzs_adapt_workspace_bytes(C.byref(self.cfg))
         self.workspace = torch.zeros(max(int(ws), 8) // 8 + 1, **f64)
         self.colsum, self.colsq = torch.zeros(d, **f64), torch.zeros(d, **f64)
@@ -270,7 +273,9 @@ class DreamEngine:
                               gauss_L=p(self.gauss_L) if self.gauss_L is not None else None,
                               gauss_U=p(self.gauss_U) if self.gauss_U is not None else None,
                               sync_ws=p(self.sync_ws) if self.sync_ws is not None and self.persistent else None,
-                              sync_ws_words=self.sync_ws.numel() if self.sync_ws is not None and self.persistent else 0)
+                              sync_ws_words=self.sync_ws.numel() if self.sync_ws is not None and self.persistent else 0,
+                              draw_ws=p(self.draw_ws) if self.draw_ws is not None else None,
+                              draw_ws_bytes=self.draw_ws.numel() * 8 if self.draw_ws is not None else 0)
 
     def _ensure_capacity(self, rows):
         """Make room for `rows` archive rows.  Collective when the archive is shared between ranks."""

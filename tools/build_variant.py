@@ -18,6 +18,25 @@ def main():
     B.build()
     out = os.path.join(ROOT, 'build', 'variants')
     os.makedirs(out, exist_ok=True)
+    if any(x.startswith('-DDZ_MTP') for x in defs):     # variants of the point-parallel multi-try kernel
+        objs = [os.path.join(B.OBJ, f) for f in sorted(os.listdir(B.OBJ)) if f.endswith('.o') and not f.startswith('mtp_')]
+        mine = []
+        for g in B.MTP_VARIANTS:
+            o = os.path.join(out, '%s_mtp_%d.o' % (name, g))
+            cmd = [B._nvcc()] + B.NVCC_FLAGS + ['-DDZ_G=%d' % g] + defs + ['-c', os.path.join(B.CSRC, 'dreamzs_mtp_inst.cu'), '-o', o]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            if p.returncode != 0:
+                raise SystemExit(p.stdout + p.stderr)
+            for line in p.stderr.splitlines():
+                if 'spill' in line or 'registers' in line:
+                    print(line.strip()[:160])
+            mine.append(o)
+        lib = os.path.join(out, 'libdreamzs_%s.so' % name)
+        subprocess.check_call([B._nvcc(), '-shared', '-o', lib] + objs + mine + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+        for o in mine:
+            os.remove(o)
+        print(lib)
+        return
     if any(x.startswith('-DDZ_WW') for x in defs):      # variants of the whitened window kernel
         objs = [os.path.join(B.OBJ, f) for f in sorted(os.listdir(B.OBJ)) if f.endswith('.o') and f != 'dreamzs_wwin_inst.o']
         o = os.path.join(out, '%s_wwin.o' % name)
