@@ -124,44 +124,56 @@ __device__ __noinline__ bool mtp_batch(const Ctx<G, 1> &c, Stream &s, const Deci
 // What one multi-try iteration decides (the state update itself is mt_commit)
 struct MtOutcome { int sel; bool gamma_one, accepted; double new_prior, new_like; };
 
+// The multi-try selection and acceptance arithmetic is a handful of exp / log / divide on k (or 2k) numbers.  Every lane
+// of the warp would compute all of them -- and on B200 a warp-wide fp64 instruction costs the same two issue cycles of
+// the one fp64 pipe whether one lane needs it or 32 -- so lane l computes the l-th exponential only and the values are
+// exchanged by shuffles; the sums run in the reference's order on every lane (same bits everywhere).
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
 // mt_choose_proposal_pt (Dream.py:883-917) given the uniform of the multinomial draw: inverse CDF on a running sum
-__device__ __forceinline__ int mt_choose(const double *pri, const double *lik, double Tc, int k, double u) {
+__device__ __forceinline__ int mt_choose(const double *pri, const double *lik, double Tc, int k, double u, int lane) {
   double mx = Tc * lik[0] + pri[0];
   for (int p = 1; p < k; ++p) { const double v = Tc * lik[p] + pri[p]; if (v > mx) mx = v; }
-  double prob[DREAMZS_MAX_MULTITRY / 2], sum = 0.0;
-  for (int p = 0; p < k; ++p) { prob[p] = exp((Tc * lik[p] + pri[p]) - mx); sum = (p == 0) ? prob[0] : sum + prob[p]; }
+  const int lp = lane < k ? lane : 0;
+  const double e = exp((Tc * lik[lp] + pri[lp]) - mx);        // lane p: exp(log_ps[p] - max)
+  double sum = 0.0;
+  for (int p = 0; p < k; ++p) { const double ep = shfl_d(e, p); sum = (p == 0) ? ep : sum + ep; }
+  const double pr = e / sum;                                   // lane p: the probability of point p
   double acc = 0.0;
   int idx = k - 1;
   bool found = false;
   for (int p = 0; p < k; ++p) {
-    acc = acc + prob[p] / sum;
+    acc = acc + shfl_d(pr, p);
     if (!found && u < acc) { idx = p; found = true; }
   }
   return idx;
 }
 
-// log of the multi-try acceptance ratio, Dream.py:304-323 (reference point k-1 is the current state)
+// log of the multi-try acceptance ratio, Dream.py:304-323 (reference point k-1 is the current state); k <= 16 lanes
 __device__ __forceinline__ double mt_ratio(const double *pri, const double *lik, const double *snk, const double *rpri,
                                            const double *rlik, const double *rsnk, double last_prior, double last_like,
-                                           double Tc, int k, bool run_snooker) {
-  double tp[DREAMZS_MAX_MULTITRY / 2], trf[DREAMZS_MAX_MULTITRY / 2];
-  double m2 = -INFINITY;
-  for (int p = 0; p < k; ++p) {
-    const double lps = Tc * lik[p] + pri[p];
-    const double rl = (p == k - 1) ? last_like : rlik[p], rp = (p == k - 1) ? last_prior : rpri[p];
-    const double rlps = Tc * rl + rp;
-    if (run_snooker) {                                                               // Dream.py:306-313
-      const double rs = (p == k - 1) ? 0.0 : rsnk[p];
-      tp[p] = lps + snk[p]; trf[p] = rlps + rs + snk[p];
-    } else { tp[p] = lps; trf[p] = rlps; }
-    if (p == 0) m2 = tp[0];
-    if (tp[p] > m2) m2 = tp[p];
-    if (trf[p] > m2) m2 = trf[p];
+                                           double Tc, int k, bool run_snooker, int lane) {
+  // lane p < k holds the proposal term of point p, lane k + p its reference term
+  const int p = lane < k ? lane : (lane < 2 * k ? lane - k : 0);
+  const double lps = Tc * lik[p] + pri[p];
+  const double rl = (p == k - 1) ? last_like : rlik[p], rp = (p == k - 1) ? last_prior : rpri[p];
+  const double rlps = Tc * rl + rp;
+  double tpv, trv;
+  if (run_snooker) {                                                                 // Dream.py:306-313
+    const double rs = (p == k - 1) ? 0.0 : rsnk[p];
+    tpv = lps + snk[p]; trv = rlps + rs + snk[p];
+  } else { tpv = lps; trv = rlps; }
+  double m2 = shfl_d(tpv, 0);
+  for (int q = 0; q < k; ++q) {
+    const double a = shfl_d(tpv, q), b = shfl_d(trv, q);
+    if (a > m2) m2 = a;
+    if (b > m2) m2 = b;
   }
+  const double ex = exp((lane < k ? tpv : trv) - m2);
   double swp = 0.0, swr = 0.0;
-  for (int p = 0; p < k; ++p) {
-    const double a = exp(tp[p] - m2), b = exp(trf[p] - m2);
-    swp = p == 0 ? a : swp + a; swr = p == 0 ? b : swr + b;
+  for (int q = 0; q < k; ++q) {
+    const double a = shfl_d(ex, q), b = shfl_d(ex, k + q);
+    swp = q == 0 ? a : swp + a; swr = q == 0 ? b : swr + b;
   }
   return nan_to_num(log(swp / swr));                                                 // Dream.py:320-323
 }
@@ -198,13 +210,13 @@ __device__ __noinline__ void mtp_iteration(const Ctx<G, 1> &c, int64_t iter, uin
   }
   {
     const uint4 w = s.block(s.n_multinomial++, ST_MULTINOMIAL, 0);
-    o.sel = mt_choose(pri, lik, Tc, k, u53_of(w.x, w.y));
+    o.sel = mt_choose(pri, lik, Tc, k, u53_of(w.x, w.y), (int)(threadIdx.x & 31));
   }
   load_slot<G, 1>(c, c.slots + (size_t)o.sel * ld, q);
   o.new_prior = pri[o.sel]; o.new_like = lik[o.sel];
   __syncwarp();   // every lane-group has read the selected point before the reference set overwrites the slots
   o.gamma_one = mtp_batch<G>(c, s, dc, k - 1, pt, M, q, slot, pp, rpri, rlik, rsnk);   // reference set, Dream.py:295-303
-  const double mr = mt_ratio(pri, lik, snk, rpri, rlik, rsnk, last_prior, last_like, Tc, k, dc.run_snooker != 0);
+  const double mr = mt_ratio(pri, lik, snk, rpri, rlik, rsnk, last_prior, last_like, Tc, k, dc.run_snooker != 0, (int)(threadIdx.x & 31));
   o.accepted = false;
   if (isfinite(mr)) o.accepted = log(uniform_scalar(s)) < mr;                        // metrop_select, :980-998
 }
@@ -326,26 +338,21 @@ __global__ void __launch_bounds__(128, DZ_MTP_MINBLOCKS) dreamzs_mtp_kernel(cons
 // (Dream.py:282-289 regenerates it, which shifts every later call number) sends that iteration through mtp_iteration.
 __host__ __device__ inline int mt2_record_doubles(int k, int ld) { return 8 + (2 * k - 1) * 2 * ld; }
 
-template <int G>
-__global__ void __launch_bounds__(256) dreamzs_mtdraw_kernel(const __grid_constant__ StepParams P) {
-  constexpr int CT = 256 / G;                      // (chain, iteration) pairs of a CTA: 2k-1 passes of 256 / G lane-groups
+// scalar draws of every (chain, iteration) pair of the window + the assembled decisions
+static __global__ void __launch_bounds__(256) dreamzs_mtdraw_scalars_kernel(const __grid_constant__ StepParams P) {
+  constexpr int CT = 64;                           // pairs of a CTA
   __shared__ uint2 scr[9 * CT];
-  __shared__ uint32_t s_dec[CT], s_gone[CT];
-  const int d = P.cfg.ndim, ld = P.cfg.ld, k = P.cfg.multitry, npts = 2 * k - 1, wn = P.niter;
+  const int k = P.cfg.multitry, wn = P.niter;
   const int ncts = P.cfg.nchains_local * wn;
   const int ct0 = blockIdx.x * CT;
   const int nct = min(CT, ncts - ct0);
-  const int S = mt2_record_doubles(k, ld);
+  const int S = mt2_record_doubles(k, P.cfg.ld);
   const uint32_t k0 = (uint32_t)P.cfg.seed, k1 = (uint32_t)(P.cfg.seed >> 32);
   const uint32_t s0 = P.cfg.snooker != 0 ? 1u : 0u, m0 = s0 + 2u;
   const int tid = threadIdx.x;
-  if (P.wait_k) {   // sharded archive: the peers' rows of the previous append must have landed in this replica
-    if (tid == 0) peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);
-    __syncthreads();
-  }
-  // ---- scalar draws, one Philox block per (kind, pair):
-  //      0 snooker, 1 CR, 2 gamma level (multinomial calls 0, s0, s0+1), 3 DE pairs (randint), 4-6 np.random.uniform()
-  //      calls 0-2, 7 / 8 the selection multinomial after DE / snooker batches (calls m0 + k / m0 + 1)
+  // one Philox block per (kind, pair):
+  //   0 snooker, 1 CR, 2 gamma level (multinomial calls 0, s0, s0+1), 3 DE pairs (randint), 4-6 np.random.uniform()
+  //   calls 0-2, 7 / 8 the selection multinomial after DE / snooker batches (calls m0 + k / m0 + 1)
   for (int task = tid; task < 9 * nct; task += 256) {
     const int kind = task / nct, cti = task - kind * nct;
     const int ct = ct0 + cti, c_local = ct / wn, itb = ct - c_local * wn;
@@ -378,57 +385,65 @@ __global__ void __launch_bounds__(256) dreamzs_mtdraw_kernel(const __grid_consta
     int delta = 1;
     if (P.cfg.nDEpairs > 1) delta = 1 + (int)(((uint64_t)scr[3 * CT + cti].x * (uint64_t)P.cfg.nDEpairs) >> 32);
     const uint32_t dec = (snk ? 1u : 0u) | ((uint32_t)cr << 1) | ((uint32_t)lvl << 5) | ((uint32_t)delta << 9);
-    s_dec[cti] = dec;
-    s_gone[cti] = 0u;
     double *rec = P.st.draw_ws + (size_t)ct * S;
     rec[0] = u53(snk ? 8 : 7);
     rec[1] = log(u53(snk ? 6 : 4));                      // the Metropolis uniform is np.random.uniform() call 2 / 0
     rec[2] = 1.2 + (2.2 - 1.2) * u53(4);                 // snooker gamma, Dream.py:618
     rec[3] = 1.2 + (2.2 - 1.2) * u53(5);
+    *reinterpret_cast<uint2 *>(rec + 4) = make_uint2(dec, 0u);   // the gamma == 1 bits are set by the points' kernel
   }
-  __syncthreads();
-  // ---- points: lane-group per (pair, point)
+}
+
+// the points: one lane-group per (pair, point), flat over the window
+template <int G>
+__global__ void __launch_bounds__(256, 4) dreamzs_mtdraw_kernel(const __grid_constant__ StepParams P) {
+  const int d = P.cfg.ndim, ld = P.cfg.ld, k = P.cfg.multitry, npts = 2 * k - 1, wn = P.niter;
+  const int S = mt2_record_doubles(k, ld);
+  const uint32_t s0 = P.cfg.snooker != 0 ? 1u : 0u, m0 = s0 + 2u;
+  const int tid = threadIdx.x;
+  if (P.wait_k) {   // sharded archive: the peers' rows of the previous append must have landed in this replica
+    if (tid == 0) peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);
+    __syncthreads();
+  }
   const int lane = tid & 31, g = lane & (G - 1);
   Ctx<G, 1> c{P, nullptr, nullptr, nullptr, G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1))), g, d, ld};
   const int i0 = 4 * g;
-  for (int unit = tid / G; unit < nct * npts; unit += 256 / G) {
-    const int cti = unit / npts, p = unit - cti * npts;
-    const int ct = ct0 + cti, c_local = ct / wn, itb = ct - c_local * wn;
-    const uint32_t dec = s_dec[cti];
-    Decisions dc;
-    dc.run_snooker = (int)(dec & 1u); dc.cr_idx = (int)((dec >> 1) & 15u); dc.lvl_idx = (int)((dec >> 5) & 15u);
-    dc.delta = (int)((dec >> 9) & 15u);
-    dc.CR = (double)(dc.cr_idx + 1) / (double)P.cfg.nCR;
-    Stream s; s.init(P.cfg.seed, (uint32_t)(P.cfg.chain_begin + c_local), (uint32_t)(P.iter_begin + itb));
-    const bool second = p >= k;
-    const int n = second ? k - 1 : k, pp = second ? p - k : p;
-    double A[1][4], B[1][4];
-    if (dc.run_snooker) {
-      const Bases b = {second ? 3u * (uint32_t)k : 0u, 0u, 0u};
-      snooker_rows<G, 1>(c, s, b, n, pp, P.archive_rows, A, B);
-    } else {
-      // call numbers of the batch: samples / normals from b.s = b.n, uniforms from b.u, the gamma-unity multinomial
-      const Bases b = {second ? (uint32_t)k : 0u, second ? (uint32_t)k : 0u, second ? 2u * (uint32_t)k : 0u};
-      s.n_multinomial = (second ? m0 + (uint32_t)k + 1u : m0) + (uint32_t)pp;
-      unsigned reset;
-      bool gone = false;
-      de_draw<G, 1>(c, s, dc, b, n, pp, P.archive_rows, A, B, reset, gone);
+  const int64_t unit = (int64_t)blockIdx.x * (256 / G) + tid / G;
+  if (unit >= (int64_t)P.cfg.nchains_local * wn * npts) return;     // (whole lane-groups leave together)
+  const int ct = (int)(unit / npts), p = (int)(unit - (int64_t)ct * npts);
+  const int c_local = ct / wn, itb = ct - c_local * wn;
+  double *rec = P.st.draw_ws + (size_t)ct * S;
+  const uint32_t dec = *reinterpret_cast<const uint32_t *>(rec + 4);
+  Decisions dc;
+  dc.run_snooker = (int)(dec & 1u); dc.cr_idx = (int)((dec >> 1) & 15u); dc.lvl_idx = (int)((dec >> 5) & 15u);
+  dc.delta = (int)((dec >> 9) & 15u);
+  dc.CR = (double)(dc.cr_idx + 1) / (double)P.cfg.nCR;
+  Stream s; s.init(P.cfg.seed, (uint32_t)(P.cfg.chain_begin + c_local), (uint32_t)(P.iter_begin + itb));
+  const bool second = p >= k;
+  const int n = second ? k - 1 : k, pp = second ? p - k : p;
+  double A[1][4], B[1][4];
+  if (dc.run_snooker) {
+    const Bases b = {second ? 3u * (uint32_t)k : 0u, 0u, 0u};
+    snooker_rows<G, 1>(c, s, b, n, pp, P.archive_rows, A, B);
+  } else {
+    // call numbers of the batch: samples / normals from b.s = b.n, uniforms from b.u, the gamma-unity multinomial
+    const Bases b = {second ? (uint32_t)k : 0u, second ? (uint32_t)k : 0u, second ? 2u * (uint32_t)k : 0u};
+    s.n_multinomial = (second ? m0 + (uint32_t)k + 1u : m0) + (uint32_t)pp;
+    unsigned reset;
+    bool gone = false;
+    de_draw<G, 1>(c, s, dc, b, n, pp, P.archive_rows, A, B, reset, gone);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (((reset >> j) & 1u) || i0 + j >= d) { A[0][j] = 0.0; B[0][j] = 0.0; }
-      if (gone && g == 0) atomicOr(s_gone + cti, 1u << p);
-    }
-    if (i0 < ld) {
-      double *rec = P.st.draw_ws + (size_t)ct * S + 8 + (size_t)p * 2 * ld + i0;
-      *reinterpret_cast<double2 *>(rec) = make_double2(A[0][0], A[0][1]);
-      *reinterpret_cast<double2 *>(rec + 2) = make_double2(A[0][2], A[0][3]);
-      *reinterpret_cast<double2 *>(rec + ld) = make_double2(B[0][0], B[0][1]);
-      *reinterpret_cast<double2 *>(rec + ld + 2) = make_double2(B[0][2], B[0][3]);
-    }
+    for (int j = 0; j < 4; ++j)
+      if (((reset >> j) & 1u) || i0 + j >= d) { A[0][j] = 0.0; B[0][j] = 0.0; }
+    if (gone && g == 0) atomicOr(reinterpret_cast<unsigned int *>(rec + 4) + 1, 1u << p);
   }
-  __syncthreads();
-  if (tid < nct)
-    *reinterpret_cast<uint2 *>(P.st.draw_ws + (size_t)(ct0 + tid) * S + 4) = make_uint2(s_dec[tid], s_gone[tid]);
+  if (i0 < ld) {
+    double *rp = rec + 8 + (size_t)p * 2 * ld + i0;
+    *reinterpret_cast<double2 *>(rp) = make_double2(A[0][0], A[0][1]);
+    *reinterpret_cast<double2 *>(rp + 2) = make_double2(A[0][2], A[0][3]);
+    *reinterpret_cast<double2 *>(rp + ld) = make_double2(B[0][0], B[0][1]);
+    *reinterpret_cast<double2 *>(rp + ld + 2) = make_double2(B[0][2], B[0][3]);
+  }
 }
 
 // one batch of the chain kernel: lane-group pt assembles point pt from the record, bounds, log-density
@@ -473,6 +488,8 @@ __global__ void __launch_bounds__(128, DZ_MTP_MINBLOCKS) dreamzs_mtchain_kernel(
   for (int it = 0; it < P.niter; ++it, rec += S) {
     const int64_t iter = P.iter_begin + it;
     // the record: scalars, this lane-group's proposal and reference point (neither depends on the chain state)
+    if (it + 1 < P.niter)   // the next record: on its way to L1 while this iteration runs
+      for (int o = lane * 16; o < S; o += 32 * 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + S + o));
     const double u_sel = rec[0], logu = rec[1], g1 = rec[2], g2 = rec[3];
     const uint2 wd = *reinterpret_cast<const uint2 *>(rec + 4);
     double A1[1][4] = {{0, 0, 0, 0}}, B1[1][4] = {{0, 0, 0, 0}}, A2[1][4] = {{0, 0, 0, 0}}, B2[1][4] = {{0, 0, 0, 0}};
@@ -496,18 +513,29 @@ __global__ void __launch_bounds__(128, DZ_MTP_MINBLOCKS) dreamzs_mtchain_kernel(
     dc.CR = (double)(dc.cr_idx + 1) / (double)P.cfg.nCR;
     Stream s; s.init(P.cfg.seed, c_global, (uint32_t)iter);      // (only the boundary redraws draw here)
     MtOutcome o;
-    double q[1][4];
-    mt2_batch<G>(c, s, dc.run_snooker != 0, g1, k, pt, x0, A1, B1, slot, pri, lik, snk);
-    bool anyfinite = false;
-    for (int p = 0; p < k; ++p) anyfinite |= isfinite(Tc * lik[p] + pri[p]);
-    if (anyfinite) {
-      o.sel = mt_choose(pri, lik, Tc, k, u_sel);
-      load_slot<G, 1>(c, c.slots + (size_t)o.sel * ld, q);
-      o.new_prior = pri[o.sel]; o.new_like = lik[o.sel];
-      __syncwarp();   // every lane-group has read the selected point before the reference set overwrites the slots
-      mt2_batch<G>(c, s, dc.run_snooker != 0, g2, k - 1, pt, q, A2, B2, slot, rpri, rlik, rsnk);
+    double q[1][4] = {{x0[0][0], x0[0][1], x0[0][2], x0[0][3]}};
+    bool fast = true;
+#pragma unroll 1
+    for (int bt = 0; bt < 2; ++bt) {   // the proposals around x0, then the reference set around the selected one (one copy of the code)
+      if (bt) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { A1[0][j] = A2[0][j]; B1[0][j] = B2[0][j]; }
+      }
+      mt2_batch<G>(c, s, dc.run_snooker != 0, bt ? g2 : g1, bt ? k - 1 : k, pt, q, A1, B1, slot, bt ? rpri : pri, bt ? rlik : lik,
+                   bt ? rsnk : snk);
+      if (bt == 0) {
+        bool anyfinite = false;
+        for (int p = 0; p < k; ++p) anyfinite |= isfinite(Tc * lik[p] + pri[p]);
+        if (!anyfinite) { fast = false; break; }
+        o.sel = mt_choose(pri, lik, Tc, k, u_sel, lane);
+        load_slot<G, 1>(c, c.slots + (size_t)o.sel * ld, q);
+        o.new_prior = pri[o.sel]; o.new_like = lik[o.sel];
+        __syncwarp();   // every lane-group has read the selected point before the reference set overwrites the slots
+      }
+    }
+    if (fast) {
       o.gamma_one = dc.run_snooker ? g2 == 1.0 : ((wd.y >> k) & ((1u << (k - 1)) - 1u)) != 0u;
-      const double mr = mt_ratio(pri, lik, snk, rpri, rlik, rsnk, last_prior, last_like, Tc, k, dc.run_snooker != 0);
+      const double mr = mt_ratio(pri, lik, snk, rpri, rlik, rsnk, last_prior, last_like, Tc, k, dc.run_snooker != 0, lane);
       o.accepted = isfinite(mr) && logu < mr;                                        // metrop_select, Dream.py:980-998
     } else {
       __syncwarp();
@@ -532,9 +560,9 @@ int launch_mtp(const StepParams &P, size_t smem, cudaStream_t stream) {
     if (ensure_dynamic_smem(kern, smem, smem_set[two_stage ? 1 : 0]) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
   }
   if (two_stage) {
-    constexpr int CT = 256 / G;
-    const int ncts = P.cfg.nchains_local * P.niter;
-    dreamzs_mtdraw_kernel<G><<<(ncts + CT - 1) / CT, 256, 0, stream>>>(P);
+    const int64_t ncts = (int64_t)P.cfg.nchains_local * P.niter, units = ncts * (2 * P.cfg.multitry - 1);
+    dreamzs_mtdraw_scalars_kernel<<<(unsigned)((ncts + 63) / 64), 256, 0, stream>>>(P);
+    dreamzs_mtdraw_kernel<G><<<(unsigned)((units + 256 / G - 1) / (256 / G)), 256, 0, stream>>>(P);
     if (cudaGetLastError() != cudaSuccess) return DREAMZS_E_LAUNCH;
   }
   kern<<<grid, threads, smem, stream>>>(P);

@@ -110,7 +110,10 @@ __device__ __forceinline__ void eval_logp(const Ctx<G, R> &c, const double (&x)[
       s0 = gsum<G>(s0, c.gmask); s1 = gsum<G>(s1, c.gmask);
       const double l0 = -.5 * s0 + tb[0], l1 = -.5 * s1 + tb[1];
       const double mx = l0 > l1 ? l0 : l1;
-      like = log(exp(l0 - mx) + exp(l1 - mx)) + mx;
+      if (fabs(mx) <= DBL_MAX) {       // exp(mx - mx) is exactly 1: one exponential instead of two
+        const double e = exp((l0 > l1 ? l1 : l0) - mx);
+        like = log(1.0 + e) + mx;
+      } else like = log(exp(l0 - mx) + exp(l1 - mx)) + mx;
     } break;
     case DREAMZS_TARGET_BANANA: {
       const double b = tb[0], v1 = tb[1];

@@ -57,7 +57,8 @@ def report(path, pattern=None):
                 print('  %-82s %16s %s' % (k, r[i], units[i]))
         stall = [(float(r[i]), n) for i, n in enumerate(h) if n.startswith('smsp__average_warps_issue_stalled_') and n.endswith('_per_issue_active.ratio')]
         print('  top stalls (warps per issue-active): ' + ', '.join('%s %.2f' % (n.split('stalled_')[1].split('_per_')[0], v) for v, n in sorted(stall, reverse=True)[:6]))
-        break
+        if pattern is not None:
+            break
     src = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--launch-count', '1'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     hi = next(i for i, r in enumerate(rows) if 'Instructions Executed' in r)
@@ -71,7 +72,10 @@ def report(path, pattern=None):
         if not t:
             continue
         o = t[1] if t[0].startswith('@') and len(t) > 1 else t[0]
-        ops[o.split('.')[0]] += int(r[ia])
+        try:
+            ops[o.split('.')[0]] += int(r[ia])
+        except ValueError:      # header row of a further kernel
+            break
     tot = sum(ops.values())
     print('  SASS warp-instructions executed (first launch): %d' % tot)
     print('  ' + ', '.join('%s %.1f%%' % (o, 100 * n / tot) for o, n in ops.most_common(14)))
