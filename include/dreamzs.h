@@ -47,6 +47,7 @@ extern "C" {
 #define DREAMZS_MAX_NDIM 1024
 #define DREAMZS_GAUSS_REFRESH_WINDOWS 4
 #define DREAMZS_MAX_PEERS 8
+#define DREAMZS_SYNC_GROUP_WORDS 4096
 
 /* dreamzs_config.flags */
 #define DREAMZS_FLAG_ALL_FLAT 1  /* every prior is FLAT: the kernels skip prior evaluation and bounds */
@@ -127,9 +128,10 @@ typedef struct dreamzs_state {
   const double *gauss_L;
   double *gauss_U;
   /* Optional (may be NULL): scratch words for launches that span several windows (dreamzs_run with the whitened
-   * window kernel): 16 + (windows per launch) uint32.  With it dreamzs_run issues ONE persistent launch for a whole
-   * span of iterations; the CTAs synchronise through these words only where a sampled row was appended inside the
-   * launch.  Without it every window is its own launch. */
+   * window kernel): 16 + 2 (windows per launch + 2) + DREAMZS_SYNC_GROUP_WORDS uint32.  With it dreamzs_run issues ONE
+   * persistent launch for a whole span of iterations; the CTAs synchronise through these words only where a sampled
+   * row was appended inside the launch (per window, and -- in the last DREAMZS_SYNC_GROUP_WORDS words -- per group of
+   * chains that shares a CTA).  Without it every window is its own launch. */
   uint32_t *sync_ws;
   int64_t sync_ws_words;
   /* Optional (may be NULL): scratch of the two-stage multi-try step (multitry > 1, ld <= 32, multitry <= 8 / (ld > 16 ? 2 : 1)):
@@ -254,7 +256,17 @@ typedef struct dreamzs_peers {
   uint64_t *flags[DREAMZS_MAX_PEERS];
   uint32_t *counter;         /* device uint32 of this rank, zero-initialised: chains that have appended (scratch) */
   int32_t *error;            /* device int32 of this rank, zero-initialised; 1 after a timed-out wait */
+  /* 0, or the length of the per-group progress rows that follow the append flags in every rank's block: from
+   * flags[q] + DREAMZS_GFLAG_OFFSET on, world rows of gflag_stride uint64 (zero-initialised); rank q uses row q of ITS
+   * OWN block: word g = appends the chains of its group g (the chains that share a CTA) have completed.  Launches that
+   * span several windows push appended rows to the peers without a system-scope fence on the chains' path; a block is
+   * confirmed in flags[q][rank] once per append by one thread.  A reader that samples a peer's row before its block is
+   * confirmed polls that group's word in the OWNER's memory and fetches the row from the owner's archive (both over
+   * NVLink), so it waits for the chains that write the row and for nothing else. */
+  int32_t gflag_stride;
+  int32_t reserved;
 } dreamzs_peers;
+#define DREAMZS_GFLAG_OFFSET 512   /* uint64 words from flags[q] to the per-group flag rows */
 #define DREAMZS_PEER_TIMEOUT_NS 10000000000ull
 
 /* Device memory that other processes of the box can map: cudaMalloc + cudaIpcGetMemHandle (zero-filled),

@@ -51,11 +51,13 @@ class Trace(C.Structure):
 
 
 MAX_PEERS = 8
+GFLAG_OFFSET = 512          # uint64 words from a rank's append flags to its per-group flag rows (include/dreamzs.h)
+SYNC_GROUP_WORDS = 4096
 
 
 class Peers(C.Structure):
     _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('Z', C.c_void_p * MAX_PEERS), ('flags', C.c_void_p * MAX_PEERS),
-                ('counter', C.c_void_p), ('error', C.c_void_p)]
+                ('counter', C.c_void_p), ('error', C.c_void_p), ('gflag_stride', C.c_int32), ('reserved', C.c_int32)]
 
 
 APPEND_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64)

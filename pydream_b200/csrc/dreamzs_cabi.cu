@@ -239,7 +239,7 @@ static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const d
     // only the last iteration of a launch may append (the archive is read-only inside a launch)
     for (int it = 0; it + 1 < niter; ++it)
       if ((iter_begin + it) % cfg->history_thin == 0) return DREAMZS_E_BADARG;
-  } else if (!st->sync_ws || 2 * (appends_between(iter_begin, niter, cfg->history_thin) + 2) + 16 > st->sync_ws_words) return DREAMZS_E_BADARG;
+  } else if (!st->sync_ws || 2 * (appends_between(iter_begin, niter, cfg->history_thin) + 2) + 16 + DREAMZS_SYNC_GROUP_WORDS > st->sync_ws_words) return DREAMZS_E_BADARG;
   if (archive_rows + appends_between(iter_begin, niter, cfg->history_thin) * cfg->nchains_global > st->Z_capacity_rows)
     return DREAMZS_E_BADARG;
   if (niter == 0 || cfg->nchains_local == 0) return DREAMZS_OK;
@@ -249,8 +249,9 @@ static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const d
   if (multi) {
     P.ww_sync = st->sync_ws; P.ww_k0 = k0;
     P.ww_wcap = (int32_t)appends_between(iter_begin, niter, cfg->history_thin) + 2;
-    // abort word + two counters per appending window of the span (chains appended / forwarded to the peers), zeroed in stream order
-    const size_t words = 16 + 2 * (size_t)P.ww_wcap;
+    // abort word + two counters per appending window of the span (chains appended / forwarded to the peers) + the
+    // per-group counters at the end, zeroed in stream order
+    const size_t words = (size_t)st->sync_ws_words;
     if (cudaMemsetAsync(st->sync_ws, 0, words * sizeof(uint32_t), (cudaStream_t)stream) != cudaSuccess) { (void)cudaGetLastError(); return DREAMZS_E_LAUNCH; }
   }
   if (temperature) {   // only the generic kernel scales the log-likelihood; the dense-Gaussian kernels assume T = 1
@@ -268,6 +269,13 @@ static int step_impl(const dreamzs_config *cfg, const dreamzs_state *st, const d
       }
     if (!peers->flags[peers->rank] || !peers->counter || !peers->error) return DREAMZS_E_BADARG;
     P.my_flags = peers->flags[peers->rank]; P.my_rank = peers->rank; P.world = peers->world;
+    if (multi && peers->gflag_stride > 0) {
+      P.gflag_stride = peers->gflag_stride;
+      P.my_pub = peers->flags[peers->rank] + DREAMZS_GFLAG_OFFSET + (size_t)peers->rank * peers->gflag_stride;
+      int np = 0;
+      for (int q = 0; q < peers->world; ++q)
+        if (q != peers->rank) P.peer_pub[np++] = peers->flags[q] + DREAMZS_GFLAG_OFFSET + (size_t)q * peers->gflag_stride;
+    }
     P.wait_k = wait_k; P.publish_k = publish_k; P.peer_counter = peers->counter; P.peer_error = peers->error;
   }
   return dispatch(P, (cudaStream_t)stream);
@@ -331,7 +339,7 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
   }
   // whitened window kernel with scratch words: ONE persistent launch per span of windows (up to the scratch size)
   bool persistent = false;
-  if (st->sync_ws && st->sync_ws_words > 32 && !hook) {
+  if (st->sync_ws && st->sync_ws_words > 32 + DREAMZS_SYNC_GROUP_WORDS && !hook) {
     StepParams Q{};
     Q.cfg = *cfg; Q.st = *st; Q.all_flat = all_flat_hint(cfg);
     persistent = check_cfg(cfg, st) == DREAMZS_OK && wwin_eligible(Q);
@@ -343,7 +351,7 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
     if (burn) n = 1;
     if (persistent && !burn) {
       // as many whole windows as the scratch words allow
-      const int64_t maxwin = (st->sync_ws_words - 32) / 2 - 2;
+      const int64_t maxwin = (st->sync_ws_words - DREAMZS_SYNC_GROUP_WORDS - 32) / 2 - 2;
       int64_t span = end - t;
       if (appends_between(t, span, thin) > maxwin) span = (nxt + (maxwin - 1) * thin + 1) - t;
       const int64_t napp = appends_between(t, span, thin);

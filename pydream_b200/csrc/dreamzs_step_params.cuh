@@ -4,13 +4,6 @@
 
 namespace dreamzs {
 
-// shared-memory carve-up of the dataflow form of the whitened window kernel (dreamzs_wflow_kernel.cuh wflow_layout)
-struct WflowLayout {
-  int32_t nch, nI, nK, ntilesL, ncolmax, ntmax;
-  int32_t oL, oW, oJ, oN, oGam, oScr, oLogu, oGsn, oRows, oMeta, oDpr, oMask, oMbar, oUses, oProbs, oSync, oPool, npool, bytes;
-  uint32_t m_nch;
-};
-
 // shared-memory carve-up of the whitened window kernel (byte offsets; dreamzs_wwin_kernel.cuh wwin_layout)
 struct WwinLayout {
   int32_t nch, nI, nK, ntilesL, ncolmax;
@@ -49,9 +42,15 @@ struct StepParams {
   int32_t gw_append;      // window kernel: the last iteration of the launch appends to the archive
   int32_t gw_refresh;     // window kernel: re-derive gauss_Y / gauss_Q from X at the start of the launch
   WwinLayout ww_L;
-  WflowLayout wf_L;
   int32_t ww_tc, ww_nb, ww_nsplit, ww_isplit[5];
   uint32_t *ww_sync;      // != NULL: the launch spans several windows; word 0 abort flag, words 16.. chains that made append #j
+  uint32_t *ww_gdone;     // != NULL: per group of ww_tc chains, the appends its chains have made in this launch (summed over the chains)
+  // per-group progress words (dreamzs_peers.gflag_stride): my_pub[g] = appends group g of THIS rank has completed since the
+  // start of the run (written here, in this rank's own memory); peer_pub[pz] = the same words of peer pz, read over NVLink
+  uint64_t *my_pub;
+  const uint64_t *peer_pub[DREAMZS_MAX_PEERS];
+  int32_t gflag_stride;
+  int32_t ww_confirm;     // the launch's last CTA confirms this rank's appended blocks to the peers (dreamzs_wwin_kernel.cuh)
   int32_t ww_wcap;        // windows the scratch words hold: counters[ww_wcap] chains appended, then [ww_wcap] chains forwarded to the peers
   uint64_t ww_k0;         // appends made before this launch (peer flags count appends from the start of the run)   // whitened window kernel: chains per CTA, iterations per batch, i-tile ranges of the products
   const double *temperature;   // [nchains_local] per-chain temperature T of astep(q0, T, ...) (Dream.py:193); NULL = 1

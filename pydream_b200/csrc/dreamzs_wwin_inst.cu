@@ -1,6 +1,6 @@
 // Whitened window kernel (dreamzs_wwin_kernel.cuh): instantiations per lanes-per-chain, launch plan, whitening refresh.
 #include <stdlib.h>
-#include "dreamzs_wflow_kernel.cuh"
+#include "dreamzs_wwin_kernel.cuh"
 
 using namespace dreamzs;
 
@@ -33,38 +33,17 @@ static const WwinPlan &cached_plan(const dreamzs_config &cfg, int sms, int niter
 
 int dreamzs_wwin_usable(const dreamzs_config &cfg, int sms, int niter) { return cached_plan(cfg, sms, niter).tc > 0; }
 
-// the dataflow kernel's plan (whole windows per item); tc == 0 when a window does not fit
-static const WflowPlan &cached_flow_plan(const dreamzs_config &cfg, int sms, int wmax) {
-  thread_local struct { PlanKey key; WflowPlan plan; bool used; } slots[8] = {};
-  thread_local int next = 0;
-  const PlanKey key = {cfg.ndim, cfg.ld, cfg.nchains_local, cfg.ngamma, sms, wmax};
-  for (auto &s : slots)
-    if (s.used && s.key.ndim == key.ndim && s.key.ld == key.ld && s.key.nchains_local == key.nchains_local &&
-        s.key.ngamma == key.ngamma && s.key.sms == key.sms && s.key.niter == key.niter)
-      return s.plan;
-  auto &s = slots[next];
-  next = (next + 1) & 7;
-  s.key = key; s.used = true;
-  s.plan = wflow_plan(cfg, sms, wmax, env_int("DREAMZS_WW_TC"));
-  return s.plan;
-}
-
 int dreamzs_launch_wwin(StepParams &P, int sms, cudaStream_t stream) {
   const int wmax = P.niter < P.cfg.history_thin ? P.niter : P.cfg.history_thin;     // longest window of the launch
-  static const int flow_on = env_int("DREAMZS_WW_FLOW");   // experiments: the warp-specialised dataflow form (slower so far)
-  if (flow_on) {
-    const WflowPlan &fp = cached_flow_plan(P.cfg, sms, wmax);
-    if (fp.tc > 0) {
-      P.ww_tc = fp.tc; P.ww_nb = fp.nb; P.wf_L = fp.layout;
-      if (fp.lpc == 32) return launch_wflow_t<32>(P, fp, sms, stream);
-      if (fp.lpc == 16) return launch_wflow_t<16>(P, fp, sms, stream);
-      return launch_wflow_t<8>(P, fp, sms, stream);
-    }
-  }
   const WwinPlan &pl = cached_plan(P.cfg, sms, wmax);
   if (pl.tc == 0) return DREAMZS_E_UNSUPPORTED;
   P.ww_tc = pl.tc; P.ww_nb = pl.nb; P.ww_nsplit = pl.nsplit; P.ww_L = pl.layout;
   for (int q = 0; q <= WW_MAXSPLIT; ++q) P.ww_isplit[q] = pl.isplit[q];
+  // several windows in one launch: per-group completion counters in the last words of the scratch, per-group flags of the
+  // peers -- when the groups fit
+  const int ngroups = (P.cfg.nchains_local + pl.tc - 1) / pl.tc;
+  P.ww_gdone = (P.ww_sync && ngroups <= DREAMZS_SYNC_GROUP_WORDS) ? P.ww_sync + (P.st.sync_ws_words - DREAMZS_SYNC_GROUP_WORDS) : nullptr;
+  if (!P.ww_sync || ngroups > P.gflag_stride) { P.my_pub = nullptr; P.gflag_stride = 0; }
   if (pl.lpc == 32) return launch_wwin_t<32>(P, pl, sms, stream);
   if (pl.lpc == 16) return launch_wwin_t<16>(P, pl, sms, stream);
   return launch_wwin_t<8>(P, pl, sms, stream);

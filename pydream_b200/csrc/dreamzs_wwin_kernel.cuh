@@ -146,12 +146,31 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) {
   return v;
 }
 
-// Can archive row r be read?  Rows below the launch's archive size always can.  A row appended DURING this launch belongs
-// to append block j = (r - archive_rows) / nchains_global and to the chain (r - archive_rows) % nchains_global: it is there
-// once every local chain has made append j (counters[j] == nchains_local; each chain counts itself after its row is
-// globally visible) or, for a chain of peer rank q, once q has published append ww_k0 + j + 1 (the flag is written after
-// q's rows have reached this replica).  Gives up after DREAMZS_PEER_TIMEOUT_NS or when another CTA has aborted.
-struct RowWait {      // what row_ready needs of the launch parameters (by value: the parameter block stays in constant memory)
+// The peers' flags live in THIS GPU's memory and so do the rows they announce (the writer fences at system scope between
+// the two): for the reader a gpu-scope acquire is what orders its later reads of the rows -- through this GPU's L2 --
+// after the flag.  (ld.acquire.sys costs a system-scope fence per poll: ~14 us measured on B200, which put the pre-draw
+// warps behind the chains at 2 GPUs.)
+__device__ __forceinline__ uint64_t ld_acquire_gpu_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ uint64_t ld_relaxed_sys_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Where can archive row r be read?  Rows below the launch's archive size: in this replica.  A row appended DURING this
+// launch belongs to append block j = (r - archive_rows) / nchains_global and to the chain (r - archive_rows) % nchains_global:
+//   - a local chain: the row is there once the chains of its group (the TC chains that share a CTA) have made append j
+//     (gdone[g]: every chain counts itself after its row is visible on this GPU), or -- without per-group words -- once
+//     every local chain has (counters[j]);
+//   - a chain of peer q: in this replica once q has confirmed the block (flags, known[1 + q]); before that the row is read
+//     from q's OWN archive over NVLink as soon as q's group has completed the append (peer_pub, polled in q's memory).
+// Gives up after DREAMZS_PEER_TIMEOUT_NS or when another CTA has aborted.
+struct RowWait {      // what row_source needs of the launch parameters (by value: the parameter block stays in constant memory)
   int64_t archive_rows;
   int32_t nchains_global, chain_begin, nchains_local;
   uint64_t k0;
@@ -160,46 +179,72 @@ struct RowWait {      // what row_ready needs of the launch parameters (by value
   const uint32_t *counters;
   volatile int32_t *status;
   long long *dbg;       // profiling aid: [66] cycles spent waiting for rows, [67] waits
+  const uint32_t *gdone;
+  int32_t tc, rank;
+  const uint64_t *peer_pub[DREAMZS_MAX_PEERS];
 };
-__device__ __noinline__ bool row_wait(const RowWait w, int j, bool local, int q) {
+constexpr int ROW_SRC_SHIFT = 48;      // a row index carries its source above bit 48: 0 this replica, 1 + pz peer pz's archive
+__device__ __noinline__ bool row_wait(const RowWait w, int j, bool local, int q, int grp, const uint64_t *pub) {
   const uint64_t k = w.k0 + (uint64_t)j + 1u;
+  const uint32_t need = (uint32_t)(j + 1) * (uint32_t)min(w.tc, w.nchains_local - grp * w.tc);   // (local groups)
   const uint64_t t0 = globaltimer_ns();
   for (;;) {
-    if (local ? ld_acquire_gpu_u32(w.counters + j) >= (uint32_t)w.nchains_local : ld_acquire_sys(w.my_flags + q) >= k) return true;
+    if (pub) { if (ld_relaxed_sys_u64(pub + grp) >= k) return true; }
+    else if (local && w.gdone) { if (ld_acquire_gpu_u32(w.gdone + grp) >= need) return true; }
+    else if (local ? ld_acquire_gpu_u32(w.counters + j) >= (uint32_t)w.nchains_local : ld_acquire_gpu_u64(w.my_flags + q) >= k) return true;
     if (*w.status != 0) return false;
     if (globaltimer_ns() - t0 > DREAMZS_PEER_TIMEOUT_NS) {
       atomicExch(const_cast<int32_t *>(w.status), 1);
       if (w.peer_error) atomicExch(w.peer_error, 1);
       return false;
     }
-    __nanosleep(200);
+    __nanosleep(32);
   }
 }
 // `known` (shared memory, zeroed per launch): known[0] = leading append blocks of this launch known complete for the local
-// chains, known[1 + q] = the same for peer q (a writer completes its blocks in order), so that only the first reader of a
-// block pays for the acquire load
-__device__ __forceinline__ bool row_ready(const RowWait &w, int *known, int64_t r) {
-  if (r < w.archive_rows || !w.counters) return true;
+// chains, known[1 + q] = the same for peer q's rows in this replica (brought up to date once per batch by known_refresh).
+// Returns -1 (timed out / aborted), 0 (this replica) or 1 + pz (peer pz's archive).
+__device__ __forceinline__ int row_source(const RowWait &w, int *known, int64_t r) {
+  if (r < w.archive_rows || !w.counters) return 0;
   const int64_t off = r - w.archive_rows;
   const int j = (int)(off / w.nchains_global);
   const int owner = (int)(off - (int64_t)j * w.nchains_global);
   const bool local = owner >= w.chain_begin && owner < w.chain_begin + w.nchains_local;
   const int q = local ? 0 : owner / w.nchains_local;
   int *kn = known + (local ? 0 : 1 + q);
-  if (j < *reinterpret_cast<volatile int *>(kn)) return true;
+  if (j < *reinterpret_cast<volatile int *>(kn)) return 0;
+  const int pz = q < w.rank ? q : q - 1;
+  const uint64_t *pub = local ? nullptr : w.peer_pub[pz];
+  const int grp = w.tc > 0 ? (owner - (local ? w.chain_begin : q * w.nchains_local)) / w.tc : 0;
   const long long t0 = w.dbg ? clock64() : 0;
-  if (!row_wait(w, j, local, q)) return false;
+  if (!row_wait(w, j, local, q, grp, pub)) return -1;
   if (w.dbg) { atomicAdd(reinterpret_cast<unsigned long long *>(w.dbg) + 66, (unsigned long long)(clock64() - t0)); atomicAdd(reinterpret_cast<unsigned long long *>(w.dbg) + 67, 1ull); }
-  atomicMax(kn, j + 1);
-  return true;
+  if (pub) { __threadfence(); return 1 + pz; }
+  if (!(local && w.gdone)) atomicMax(kn, j + 1);     // whole-block wait: everything up to j is there
+  return 0;
 }
-__device__ __forceinline__ bool rows_ready(const RowWait &w, int *known, int64_t ra, int64_t rb, int64_t rc) {
-  bool ok = row_ready(w, known, ra);
-  ok = row_ready(w, known, rb) && ok;
-  if (rc >= 0) ok = row_ready(w, known, rc) && ok;
-  return ok;
+// true when row r lies in a block appended during this launch that is not known complete yet (shared-memory test only)
+__device__ __forceinline__ bool row_maybe_late(const RowWait &w, const int *known, int64_t r) {
+  if (r < w.archive_rows || !w.counters) return false;
+  const int64_t off = r - w.archive_rows;
+  const int j = (int)(off / w.nchains_global);
+  const int owner = (int)(off - (int64_t)j * w.nchains_global);
+  const bool local = owner >= w.chain_begin && owner < w.chain_begin + w.nchains_local;
+  return j >= *reinterpret_cast<const volatile int *>(known + (local ? 0 : 1 + owner / w.nchains_local));
 }
-
+// one thread, once per batch: how many leading blocks of this launch are complete by now (blocks [0, nblk) exist)
+__device__ __forceinline__ void known_refresh(const RowWait &w, int *known, int nblk, int world, int rank) {
+  if (!w.counters) return;
+  int k = known[0];
+  while (k < nblk && ld_acquire_gpu_u32(w.counters + k) >= (uint32_t)w.nchains_local) ++k;
+  if (k > known[0]) atomicMax(known, k);
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) continue;
+    const uint64_t f = ld_acquire_gpu_u64(w.my_flags + q);
+    const int kq = f > w.k0 ? (int)min((uint64_t)nblk, f - w.k0) : 0;
+    if (kq > known[1 + q]) atomicMax(known + 1 + q, kq);
+  }
+}
 #ifndef DZ_WW_MINBLOCKS
 #define DZ_WW_MINBLOCKS 1
 #endif
@@ -239,12 +284,12 @@ __device__ __forceinline__ void ww_first(WwItem &w, const StepParams &P, int TC,
   w.blk = 0; w.grp = blockIdx.x; w.done = 0; w.seq = 0; w.first_window = true;
   ww_derive(w, P, TC, NB);
 }
-__device__ __forceinline__ void ww_next(WwItem &w, const StepParams &P, int TC, int NB, int ngroups) {
+__device__ __forceinline__ void ww_next(WwItem &w, const StepParams &P, int TC, int NB, int ngroups, int nwork) {
   w.seq += 1;
   w.done += w.nb;
   if (w.done >= w.wn) {            // next group of the window; after the last one the next window
     w.done = 0;
-    w.grp += gridDim.x;
+    w.grp += nwork;
     if (w.grp >= ngroups) {
       w.grp = blockIdx.x;
       w.first_window = false;
@@ -284,17 +329,41 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
   double *pool = reinterpret_cast<double *>(smem_raw + L.oPool);
   int *pool_n = reinterpret_cast<int *>(probs + 34);          // snooker columns of the batch that hold a pool slot
   int *known = reinterpret_cast<int *>(probs + 35);           // [1 + DREAMZS_MAX_PEERS] append blocks known complete (row_ready)
+  int *fwd_cnt = reinterpret_cast<int *>(probs + 44);         // chains of the group whose appended row is in the archive (peer forwarding)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double logF = P.st.target_table[0];
   int dbg_n = 0;
 #define WW_STAMP() do { if (P.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 60) P.dbg[dbg_n] = clock64(); ++dbg_n; } while (0)
   WW_STAMP();   // 0: kernel entry
+  if (P.ww_confirm && blockIdx.x == gridDim.x - 1) {
+    // ---- the confirmer: several GPUs, several windows per launch.  The chains push their appended rows to the peers'
+    // replicas and fence at GPU scope only; for every append of the launch this one thread waits until all local chains
+    // have counted themselves, fences ONCE at system scope (~14 us on B200 -- on nobody's path here) and tells every peer
+    // "block #k of this rank is in your replica".  Until then the peers fetch those rows from this rank's archive.
+    if (threadIdx.x == 0) {
+      const uint32_t *cnt = P.ww_sync + 16;
+      const volatile int32_t *st = reinterpret_cast<const volatile int32_t *>(P.ww_sync);
+      const int napp = P.ww_wcap - 2;
+      for (int j = 0; j < napp; ++j) {
+        const uint64_t t0 = globaltimer_ns();
+        while (ld_acquire_gpu_u32(cnt + j) < (uint32_t)P.cfg.nchains_local) {
+          if (*st != 0 || globaltimer_ns() - t0 > 4 * DREAMZS_PEER_TIMEOUT_NS) return;
+          __nanosleep(200);
+        }
+        __threadfence_system();
+        for (int pz = 0; pz < P.npeers; ++pz)
+          atomicMax_system(reinterpret_cast<unsigned long long *>(P.peer_flag[pz]), (unsigned long long)(P.ww_k0 + (uint64_t)j + 1u));
+      }
+    }
+    return;
+  }
 
   const uint32_t row_bytes = (uint32_t)ld * 8u;
   const uint32_t s0 = P.cfg.snooker != 0 ? 1u : 0u;   // multinomial call number of the CR draw
   const uint32_t k0 = (uint32_t)P.cfg.seed, k1 = (uint32_t)(P.cfg.seed >> 32);
   const int ngroups = (P.cfg.nchains_local + TC - 1) / TC;          // groups of TC chains; a CTA takes groups blockIdx.x, + gridDim.x, ...
-  const bool resident = ngroups <= (int)gridDim.x;                  // one group per CTA: chain states stay in shared memory
+  const int nwork = (int)gridDim.x - (P.ww_confirm ? 1 : 0);       // CTAs that walk chain groups (the last one may be the confirmer)
+  const bool resident = ngroups <= nwork;                           // one group per CTA: chain states stay in shared memory
   volatile int32_t *status = reinterpret_cast<volatile int32_t *>(P.ww_sync);     // word 0: != 0 aborts the launch
   uint32_t *counters = P.ww_sync ? P.ww_sync + 16 : nullptr;                     // chains that have made append #j of this launch
   constexpr int CPW = 32 / LPC;                                     // chains per warp in the chain phase
@@ -336,8 +405,14 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
   WW_STAMP();   // 1: prologue done
   bool factor_ready = false;
   long long tprev = (P.dbg && tid == 0) ? clock64() : 0;
-  const RowWait rw = {P.archive_rows, P.cfg.nchains_global, P.cfg.chain_begin, P.cfg.nchains_local, P.ww_k0, P.my_flags,
-                      P.peer_error, counters, status, P.dbg};
+  RowWait rw = {P.archive_rows, P.cfg.nchains_global, P.cfg.chain_begin, P.cfg.nchains_local, P.ww_k0, P.my_flags,
+                P.peer_error, counters, status, P.dbg, P.ww_gdone, TC, P.my_rank, {}};
+  for (int pz = 0; pz < DREAMZS_MAX_PEERS; ++pz) rw.peer_pub[pz] = (P.my_pub && pz < P.npeers) ? P.peer_pub[pz] : nullptr;
+  // the archive a (tagged) row index refers to: this replica, or -- for a peer's row not yet confirmed here -- the owner's
+  auto zrow = [&](int64_t r) -> const double * {
+    const int src = (int)(r >> ROW_SRC_SHIFT);
+    return (src ? P.peer_Z[src - 1] : P.st.Z) + (size_t)(r & ((1ll << ROW_SRC_SHIFT) - 1)) * ld;
+  };
 
   // ================================================================ pre(batch): everything of a batch that needs neither
   // the column slots nor the chain state -- scalar draws, decisions, archive row indices (waiting for rows appended inside
@@ -390,6 +465,7 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
       scr[kind * NCM + col] = out;
     }
     if (ptid == 0) *pool_n = 0;
+    if (ptid == pn - 1) known_refresh(rw, known, w.blk, P.my_flags ? P.world : 0, P.my_rank);
     named_sync(bar, pn);
     // ---- one thread per column: decisions, archive rows
     for (int col = ptid; col < ncol; col += pn) {
@@ -400,17 +476,17 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
       const uint32_t use = uses[col];
       uses[col] = (unsigned char)(use + 1u);
       // meta word: bits 0-3 CR index, 4-7 gamma level, 8 snooker, 9 gamma == 1 (set in V2), 10 "not unity",
-      // 11 parity of the mbarrier phase this use of the column slot completes
+      // 11 parity of the mbarrier phase this use of the column slot completes, 12 a sampled row was appended inside this
+      // launch and is not known to be there yet (the thread that stages the column waits for it; V2 takes the column last)
       uint32_t mt = q1.x | (q2.x << 4) | (snk ? 256u : 0u) | (q3.x != 0u ? 1024u : 0u) | ((use & 1u) << 11);
       // Metropolis uniform: the 2nd np.random.uniform() after a snooker gamma, else the 1st (its log is in place)
       if (snk) logu[col] = __hiloint2double((int)u5.y, (int)u5.x);
-      bool ok;
       if (!snk) {
         const int64_t ra = (int64_t)(((uint64_t)r6.x * (uint64_t)w.M) >> 32);
         int64_t rb = (int64_t)(((uint64_t)r6.y * (uint64_t)(w.M - 1)) >> 32);
         if (rb >= ra) rb += 1;
-        rows[3 * col] = ra; rows[3 * col + 1] = rb;
-        ok = rows_ready(rw, known, ra, rb, -1);
+        rows[3 * col] = ra; rows[3 * col + 1] = rb; rows[3 * col + 2] = -1;
+        if (row_maybe_late(rw, known, ra) || row_maybe_late(rw, known, rb)) mt |= 4096u;
         dpr[col] = 0;
         gsn[col] = ((double)(q1.x + 1u) / (double)P.cfg.nCR) * 4294967296.0;   // DE column: CR 2^32 for the crossover test
       } else {
@@ -420,11 +496,10 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
         const int64_t rz = (int64_t)(((uint64_t)r6.x * (uint64_t)w.M) >> 32);
         const int64_t r1 = (int64_t)(((uint64_t)r7.x * (uint64_t)w.M) >> 32), r2 = (int64_t)(((uint64_t)r8.x * (uint64_t)w.M) >> 32);
         rows[3 * col] = rz; rows[3 * col + 1] = r1; rows[3 * col + 2] = r2;
-        ok = rows_ready(rw, known, rz, r1, r2);
+        if (row_maybe_late(rw, known, rz) || row_maybe_late(rw, known, r1) || row_maybe_late(rw, known, r2)) mt |= 4096u;
         const int slot = atomicAdd(pool_n, 1);                               // z1 - z2 goes to the pool when a slot is left
         dpr[col] = slot < L.npool ? slot : -1;
       }
-      if (!ok) probs[32] = 1.0;
       meta[col] = mt;
     }
     named_sync(bar, pn);
@@ -500,30 +575,48 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
     }
     // ---- the archive rows of the batch's columns, staged by TMA straight into the column slots:
     //      DE: z_r1 -> J slot, z_r2 -> W slot;   snooker: z -> J slot and W slot (-> L^T z)
+    // A column whose rows were appended inside this launch and may not have arrived (meta bit 12) is staged as soon as
+    // the chains that write them -- other CTAs, other GPUs -- have: its thread waits, everybody else goes on (V2 takes such
+    // columns last), so the latency of the append -> sample dependency is covered by the batch's other columns.
     for (int col = tid; col < ncol; col += WW_THREADS) {
+      const uint32_t mt = meta[col];
+      int64_t r3[3] = {rows[3 * col], rows[3 * col + 1], rows[3 * col + 2]};
+      if (mt & 4096u) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (r3[i] >= 0) {
+            const int src = row_source(rw, known, r3[i]);
+            if (src < 0) probs[32] = 1.0;   // timed out: the host raises
+            else if (src > 0) { r3[i] |= (int64_t)src << ROW_SRC_SHIFT; rows[3 * col + i] = r3[i]; }
+          }
+      }
       fence_proxy_async();   // the slots' earlier generic-proxy accesses and the acquired rows are ordered before the async copies
       mbar_expect_tx(mbar + col, 2u * row_bytes);
-      const int64_t ra = rows[3 * col], rb = (meta[col] & 256u) ? ra : rows[3 * col + 1];
-      tma_load_row(Jc + (size_t)col * ld, P.st.Z + (size_t)ra * ld, row_bytes, mbar + col);
-      tma_load_row(Wc + (size_t)col * ld, P.st.Z + (size_t)rb * ld, row_bytes, mbar + col);
+      const int64_t ra = r3[0], rb = (mt & 256u) ? ra : r3[1];
+      tma_load_row(Jc + (size_t)col * ld, zrow(ra), row_bytes, mbar + col);
+      tma_load_row(Wc + (size_t)col * ld, zrow(rb), row_bytes, mbar + col);
     }
     WW_STAMP();   // +0: rows requested
     const long long tp0 = (P.dbg && tid == 0) ? clock64() : 0;
     // ================================================================ V2: zeta, e, gamma -> J, dx in place of the rows
+    for (int pass = 0; pass < 2; ++pass)
     for (int task = tid; task < ntask; task += WW_THREADS) {
       const int col = fdiv20(task, m_nch), q = task - col * nch;
       const uint32_t mt = meta[col];
+      if (((mt >> 12) & 1u) != (uint32_t)pass) continue;      // second pass: the columns that may have had to wait
       if (mt & 256u) {   // snooker column: z1 - z2 (Dream.py:810) -> pool slot; z / L^T z arrive by TMA
+        if (pass) mbar_wait(mbar + col, (mt >> 11) & 1u);     // (the staging thread has seen all three rows by then)
         const int slot = dpr[col];
         if (slot >= 0) {
-          const double *z1 = P.st.Z + (size_t)rows[3 * col + 1] * ld + 4 * q, *z2 = P.st.Z + (size_t)rows[3 * col + 2] * ld + 4 * q;
-          const double2 p01 = __ldg(reinterpret_cast<const double2 *>(z1)), p23 = __ldg(reinterpret_cast<const double2 *>(z1) + 1);
-          const double2 q01 = __ldg(reinterpret_cast<const double2 *>(z2)), q23 = __ldg(reinterpret_cast<const double2 *>(z2) + 1);
+          // (L2 loads: a row appended during this launch must not come from a stale L1 line it shares with its neighbour)
+          const double *z1 = zrow(rows[3 * col + 1]) + 4 * q, *z2 = zrow(rows[3 * col + 2]) + 4 * q;
+          const double2 p01 = __ldcg(reinterpret_cast<const double2 *>(z1)), p23 = __ldcg(reinterpret_cast<const double2 *>(z1) + 1);
+          const double2 q01 = __ldcg(reinterpret_cast<const double2 *>(z2)), q23 = __ldcg(reinterpret_cast<const double2 *>(z2) + 1);
           double2 *bs = reinterpret_cast<double2 *>(pool + (size_t)slot * ld + 4 * q);
           bs[0] = make_double2(p01.x - q01.x, p01.y - q01.y);
           bs[1] = make_double2(p23.x - q23.x, p23.y - q23.y);
         }
-        mbar_wait(mbar + col, (mt >> 11) & 1u);
+        if (!pass) mbar_wait(mbar + col, (mt >> 11) & 1u);
         continue;
       }
       const int ch = fdiv20(col, m_nb), itb = col - ch * nb;
@@ -633,7 +726,7 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
     // ================================================================ the chains run this batch on warps [0, NCW) while the
     // other warps make the draws of the next one
     WwItem nx = it;
-    ww_next(nx, P, TC, NB, ngroups);
+    ww_next(nx, P, TC, NB, ngroups, nwork);
     if (warp >= NCW) {
       if (nx.valid && overlap) pre(nx, tid - NCW * 32, n_pre, 2);
     } else
@@ -697,9 +790,9 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
                 const double2 b23 = *reinterpret_cast<const double2 *>(pool + (size_t)slot * ld + i0 + 2);
                 b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
               } else {              // pool full: read the two rows here
-                const double *z1 = P.st.Z + (size_t)rows[3 * col + 1] * ld + i0, *z2 = P.st.Z + (size_t)rows[3 * col + 2] * ld + i0;
-                const double2 p01 = __ldg(reinterpret_cast<const double2 *>(z1)), p23 = __ldg(reinterpret_cast<const double2 *>(z1) + 1);
-                const double2 q01 = __ldg(reinterpret_cast<const double2 *>(z2)), q23 = __ldg(reinterpret_cast<const double2 *>(z2) + 1);
+                const double *z1 = zrow(rows[3 * col + 1]) + i0, *z2 = zrow(rows[3 * col + 2]) + i0;
+                const double2 p01 = __ldcg(reinterpret_cast<const double2 *>(z1)), p23 = __ldcg(reinterpret_cast<const double2 *>(z1) + 1);
+                const double2 q01 = __ldcg(reinterpret_cast<const double2 *>(z2)), q23 = __ldcg(reinterpret_cast<const double2 *>(z2) + 1);
                 b[0] = p01.x - q01.x; b[1] = p01.y - q01.y; b[2] = p23.x - q23.x; b[3] = p23.y - q23.y;
               }
             }
@@ -779,7 +872,8 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
               double *zr = P.st.Z + (size_t)(M + c_global) * ld + i0;
               *reinterpret_cast<double2 *>(zr) = make_double2(x0[0], x0[1]);
               *reinterpret_cast<double2 *>(zr + 2) = make_double2(x0[2], x0[3]);
-              if (!counters)   // one launch per window: replicas over NVLink from here (multi-window launches: pushed by one warp below)
+              // replicas over NVLink: the chain pushes its own row (its last iteration of the window is over: the
+              // system-scope fence below delays nothing but the slowest chain of the group)
                 for (int pz = 0; pz < P.npeers; ++pz) {
                   double *zp = P.peer_Z[pz] + (size_t)(M + c_global) * ld + i0;
                   *reinterpret_cast<double2 *>(zp) = make_double2(x0[0], x0[1]);
@@ -790,10 +884,21 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
           if (appending && (counters || P.publish_k)) {
             // the row is visible before the chain counts itself: to this GPU (multi-window launch: local readers watch the
             // counter), to the peers as well when the chain's warp stores the replicas itself
+            // the row is visible on this GPU before the chain counts itself.  Several windows per launch: no system-scope
+            // fence here (~14 us on B200, and every chain of the window would pay it before the CTA's next barrier): the
+            // peers read a block from their replica only after the confirmer has confirmed it, from this archive before.
             if (!counters && P.npeers) __threadfence_system(); else __threadfence();
             __syncwarp();
             if (g == 0 && valid) {
-              if (counters) atomicAdd(counters + blk, 1u);
+              if (counters) {
+                if (P.ww_gdone) atomicAdd(P.ww_gdone + it.grp, 1u);
+                if (P.my_pub && atomicAdd(fwd_cnt, 1) == nch_cta - 1) {   // last chain of the group: its progress word
+                  atomicExch(fwd_cnt, 0);
+                  __threadfence();
+                  *reinterpret_cast<volatile uint64_t *>(P.my_pub + it.grp) = P.ww_k0 + (uint64_t)blk + 1u;
+                }
+                atomicAdd(counters + blk, 1u);   // (the confirmer CTA watches this one)
+              }
               else peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
             }
           }
@@ -834,32 +939,6 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
     if (!overlap && nx.valid) {
       pre(nx, tid, WW_THREADS, 1);
       __syncthreads();
-    }
-    if (counters && P.npeers && w_append && it.last_batch && warp == WW_WARPS - 1) {
-      // Multi-window launch on several GPUs: ONE warp forwards the group's appended rows to the peers' replicas (the rows
-      // are in this GPU's archive and visible to the CTA after the barrier), fences once at system scope, counts the
-      // group and -- when this rank's block is complete -- publishes append #(k0 + blk + 1).  The other warps are already
-      // on the next batch; the system-scope fence is off every chain's path.
-      const int i0p = 4 * lane;
-      if (i0p < ld)
-        for (int cs = 0; cs < nch_cta; ++cs) {
-          const size_t row = (size_t)(M + P.cfg.chain_begin + cta_chain0 + cs) * ld + i0p;
-          const double2 a = *reinterpret_cast<const double2 *>(P.st.Z + row), b = *reinterpret_cast<const double2 *>(P.st.Z + row + 2);
-          for (int pz = 0; pz < P.npeers; ++pz) {
-            *reinterpret_cast<double2 *>(P.peer_Z[pz] + row) = a;
-            *reinterpret_cast<double2 *>(P.peer_Z[pz] + row + 2) = b;
-          }
-        }
-      __threadfence_system();
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t old = atomicAdd(counters + P.ww_wcap + blk, (uint32_t)nch_cta);
-        if (old + (uint32_t)nch_cta == (uint32_t)P.cfg.nchains_local) {
-          __threadfence_system();
-          for (int pz = 0; pz < P.npeers; ++pz)
-            atomicMax_system(reinterpret_cast<unsigned long long *>(P.peer_flag[pz]), (unsigned long long)(P.ww_k0 + blk + 1));
-        }
-      }
     }
     if (it.last_batch && (!resident || it.last_window)) {   // chain states -> global memory
       for (int i = tid; i < nch_cta * nch; i += WW_THREADS) {
@@ -975,6 +1054,7 @@ inline WwinPlan wwin_plan(const dreamzs_config &cfg, int sms, int niter_max, int
 
 template <int LPC>
 int launch_wwin_t(StepParams &P, const WwinPlan &pl, int sms, cudaStream_t stream) {
+  P.ww_confirm = 0;
   auto kern = dreamzs_wwin_kernel<LPC>;
   static size_t smem_set[64] = {0};
   if (ensure_dynamic_smem(kern, pl.smem, smem_set) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
@@ -992,7 +1072,11 @@ int launch_wwin_t(StepParams &P, const WwinPlan &pl, int sms, cudaStream_t strea
     return DREAMZS_E_LAUNCH;
   }
   const int cap = sms * per_sm;
-  const int grid = ngroups < cap ? ngroups : cap;
+  int grid = ngroups < cap ? ngroups : cap;
+  if (P.npeers > 0 && P.my_pub && cap >= 2) {   // one more CTA (or the last one) confirms this rank's blocks to the peers
+    grid = ngroups + 1 < cap ? ngroups + 1 : cap;
+    P.ww_confirm = 1;
+  }
   kern<<<grid, WW_THREADS, pl.smem, stream>>>(P);
   return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;
 }

@@ -29,8 +29,10 @@ from . import targets as T
 from .collectives import allgather_rows, allreduce_sum
 
 
-SHARED_HEADER = 4096      # bytes in front of a shared archive block: flags (8 x uint64) at 0, error word at 1024,
-                          # appended-chains counter at 2048
+GFLAG_STRIDE = 4096       # per-group flag words per peer rank (dreamzs_peers.gflag_stride)
+# bytes in front of a shared archive block: flags (8 x uint64) at 0, error word at 1024, appended-chains counter at 2048,
+# then from 8 * GFLAG_OFFSET on one row of GFLAG_STRIDE uint64 per peer rank (per-group append flags)
+SHARED_HEADER = 8 * _cabi.GFLAG_OFFSET + _cabi.MAX_PEERS * GFLAG_STRIDE * 8
 
 
 class _DevicePtr:
@@ -228,7 +230,7 @@ class DreamEngine:
                 self.gauss_L = torch.from_numpy(packed).to(self.device)
                 self.gauss_U = torch.zeros((self.Nl, self.ld), **f64)
                 # scratch of the persistent multi-window launches (dreamzs_state.sync_ws): abort word + one counter per window
-                self.sync_ws = torch.zeros(16 + 4096, dtype=torch.int32, device=self.device)
+                self.sync_ws = torch.zeros(16 + 4096 + _cabi.SYNC_GROUP_WORDS, dtype=torch.int32, device=self.device)
         self.cfg = _cabi.Config(abi_version=_cabi.ABI_VERSION, ndim=d, ld=self.ld, nchains_global=N, chain_begin=self.c0,
                                 nchains_local=self.Nl, nCR=nCR, ngamma=gamma_levels, nDEpairs=DEpairs, multitry=multitry,
                                 hardboundaries=int(bool(hardboundaries)), history_thin=self.thin,
@@ -367,6 +369,7 @@ class DreamEngine:
             pr.flags[q] = pq
         pr.counter = base.value + 2048
         pr.error = base.value + 1024
+        pr.gflag_stride = GFLAG_STRIDE
         self.peers = pr
         return block[SHARED_HEADER:].view(torch.float64).view(rows, self.ld)
 

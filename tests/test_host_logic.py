@@ -32,7 +32,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_cabi.Config) == 14 * 4 + 4 * 8 + 8
     assert C.sizeof(_cabi.State) == 22 * 8
     assert C.sizeof(_cabi.Trace) == 5 * 8
-    assert C.sizeof(_cabi.Peers) == 8 + 8 * 8 + 8 * 8 + 8 + 8
+    assert C.sizeof(_cabi.Peers) == 8 + 8 * 8 + 8 * 8 + 8 + 8 + 8
     assert C.sizeof(_cabi.Adapt) == 8 + 8 + 13 * 8
 
 
