@@ -51,17 +51,17 @@ WORKLOADS = {
     'c2': dict(label='C2: 100-D correlated Gaussian (dense precision), 1024 chains per GPU, fused DE/snooker proposal '
                      '+ logp + accept kernel', d=100, chains=1024, scaling='weak', target='gaussian', nseed=262144,
                iters_per_step=1000, opts=dict(COMMON, multitry=1), seed_dist='box',
-               kernel='dreamzs_gwin_kernel<7>'),
+               kernel='dreamzs_wwin_kernel<32>'),
     'c3': dict(label='C3: 10-D bimodal Gaussian mixture, 4096 chains per GPU, multi-try 5 + snooker', d=10, chains=4096,
                scaling='weak', target='mixture', nseed=2 ** 21, iters_per_step=100, opts=dict(COMMON, multitry=5),
-               seed_dist='normal', kernel='dreamzs_step_kernel<4,1,true>'),
+               seed_dist='normal', kernel='dreamzs_mtchain_kernel<4> (after dreamzs_mtdraw_scalars_kernel + dreamzs_mtdraw_kernel<4>, three launches per window)'),
     'c4': dict(label='C4: 200-D twisted Gaussian (banana, b=0.1), 8192 chains in total', d=200, chains=8192,
                scaling='strong', target='banana', nseed=131072, iters_per_step=100, opts=dict(COMMON, multitry=1),
                seed_dist='banana', kernel='dreamzs_step_kernel<32,2,false>'),
     'c5': dict(label='C5: 50-D correlated Gaussian, 65536 chains in total, steady-state step (crossover adaptation during '
                      'burn-in and Gelman-Rubin timed separately: burnin / rhat)', d=50, chains=65536, scaling='strong',
                target='gaussian', nseed=524288, iters_per_step=20, opts=dict(COMMON, multitry=1), seed_dist='box',
-               kernel='dreamzs_step_kernel<16,1,false>'),
+               kernel='dreamzs_wwin_kernel<16>'),
 }
 LOGP_TOL = '|dlogp| <= 1e-12 * max(1, |logp|) (relative reading of the north_star 1e-12: ulp(1e4) is 1.8e-12); decisions bit-exact'
 
@@ -506,7 +506,7 @@ def bench_gpu(args):
     kw['multitry'] = False if kw['multitry'] == 1 else kw['multitry']
 
     def e2e_run(hist_np, start_list):
-        for _ in range(2):   # warm-up: same call, results dropped (the pinned result blocks return to torch's host cache)
+        for _ in range(3):   # warm-up: same call, results dropped (the pinned result blocks return to torch's host cache)
             run_dream([pri], tgt, nchains=N, niterations=Ke, start=start_list, start_random=False, verbose=False,
                       history_file=hist_np, save_history=False, adapt_crossover=False, seed=SEED, group=group, **kw)
         barrier()
@@ -539,7 +539,10 @@ def bench_gpu(args):
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tp) and args.workload == 'c2':
             with open(tp) as f:
-                traffic = json.load(f).get('dram_bytes_per_launch')
+                tj = json.load(f)
+                traffic = tj.get('dram_bytes_per_launch')
+                if traffic is None and tj.get('dram_bytes_per_chain_step') is not None:   # per launch like `achieved`
+                    traffic = tj['dram_bytes_per_chain_step'] * Nl * K * ips / max(launches, 1)
         line = dict(metric='chain-steps/sec', value=value, unit='chain-steps/s', n_gpus=world, steps=K, warmup=W,
                     ms_per_step=ms / K, higher_is_better=True, scaling=wl['scaling'], vs_baseline=None, dtype='f64',
                     data='synthetic', repeats=len(ms_list), region_ms=[round(x, 3) for x in ms_list],
@@ -547,7 +550,7 @@ def bench_gpu(args):
                     config=config_of(wl, N, world,
                                      l2_policy='inputs larger than L2: archive >= %.0f MB, gathered rows are random'
                                                % (wl['nseed'] * ((D + 3) // 4 * 4) * 8 / 1e6),
-                                     fused_iterations_per_launch=thin, e2e_iterations=Ke, archive_replication=transport,
+                                     fused_iterations_per_launch=K * ips // max(launches, 1), e2e_iterations=Ke, archive_replication=transport,
                                      timing='median of `repeats` regions of K steps, archive rewound in between'),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit='chain-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,

@@ -344,6 +344,15 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
     Q.cfg = *cfg; Q.st = *st; Q.all_flat = all_flat_hint(cfg);
     persistent = check_cfg(cfg, st) == DREAMZS_OK && wwin_eligible(Q);
   }
+  // kernels a window launches: the two-stage multi-try step is three (scalar draws, points, chains)
+  int kern_per_window = 1;
+  {
+    StepParams Q{};
+    Q.cfg = *cfg; Q.st = *st;
+    if (check_cfg(cfg, st) == DREAMZS_OK && cfg->target_kind != DREAMZS_TARGET_EXTERNAL && mtp_eligible(Q) && st->draw_ws &&
+        st->draw_ws_bytes >= dreamzs_draw_ws_bytes(cfg, (int32_t)(thin < niter ? thin : niter)))
+      kern_per_window = 3;
+  }
   while (t < end) {
     const int64_t nxt = ((t + thin - 1) / thin) * thin;          // first appending iteration >= t
     int64_t n = (end < nxt + 1 ? end : nxt + 1) - t;
@@ -374,7 +383,7 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
                        (p2p && !waited) ? (uint64_t)appends_done : 0, (p2p && appends) ? (uint64_t)(appends_done + 1) : 0, stream);
     if (rc != DREAMZS_OK) return rc;
     waited = true;
-    ++nl;
+    nl += kern_per_window;
     if (appends) {                                               // record_history for every chain (Dream.py:919-938)
       ++appends_done;
       if (p2p) {

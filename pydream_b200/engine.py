@@ -35,6 +35,26 @@ GFLAG_STRIDE = 4096       # per-group flag words per peer rank (dreamzs_peers.gf
 SHARED_HEADER = 8 * _cabi.GFLAG_OFFSET + _cabi.MAX_PEERS * GFLAG_STRIDE * 8
 
 
+# Shared archive blocks (and the peers' mappings of them) kept between engines of the same process group: a run_dream call
+# per model fit would otherwise pay cudaMalloc + handle exchange + cudaIpcOpenMemHandle for every peer + their inverses
+# every time (tens to hundreds of ms at 4-8 GPUs).  An engine that needs no more than the cached block re-uses it after
+# zeroing its header; release_shared_cache() frees them (collective).
+_SHARED_CACHE = {}
+
+
+def release_shared_cache(lib=None):
+    """Collective over the groups that have cached blocks: unmap the peers' archives and free the shared blocks."""
+    lib = lib or _cabi.load()
+    for key in list(_SHARED_CACHE):
+        ent = _SHARED_CACHE.pop(key)
+        torch.cuda.synchronize(ent['device'])
+        torch.distributed.barrier(ent['group'])
+        for q, pq in enumerate(ent['opened']):
+            if q != ent['rank']:
+                lib.dreamzs_shared_close(C.c_void_p(pq))
+        lib.dreamzs_shared_free(C.c_void_p(ent['base']))
+
+
 class _DevicePtr:
     """Raw device memory (owned elsewhere) exposed through __cuda_array_interface__ so torch can view it."""
 
@@ -324,6 +344,27 @@ class DreamEngine:
         dist = torch.distributed
         lib = self.lib
         nbytes = SHARED_HEADER + rows * self.ld * 8
+        key = (id(self.group), self.device.index)
+        ent = _SHARED_CACHE.get(key)
+        if ent is not None and self._shared is None and ent['nbytes'] >= nbytes and ent['world'] == self.world:
+            # (every rank takes this branch together: sizes and call history are the same on all of them)
+            del _SHARED_CACHE[key]
+            block = ent['block']
+            block[:SHARED_HEADER].zero_()             # append flags, error word, counters, per-group progress words
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)                  # nobody publishes into a header that is still being zeroed
+            self._shared_new = dict(base=ent['base'], opened=ent['opened'], block=block, nbytes=ent['nbytes'])
+            self._fill_peers(ent['base'], ent['opened'])
+            cap_rows = (ent['nbytes'] - SHARED_HEADER) // (self.ld * 8)
+            return block[SHARED_HEADER:SHARED_HEADER + cap_rows * self.ld * 8].view(torch.float64).view(cap_rows, self.ld)
+        if ent is not None and self._shared is None:  # cached block too small (or of another world size): free it first
+            del _SHARED_CACHE[key]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
+            for q, pq in enumerate(ent['opened']):
+                if q != ent['rank']:
+                    lib.dreamzs_shared_close(C.c_void_p(pq))
+            lib.dreamzs_shared_free(C.c_void_p(ent['base']))
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)                      # nobody is still writing into the block being replaced
         base, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -362,16 +403,19 @@ class DreamEngine:
         if self._shared is not None:                  # growing: the flags published so far carry over
             old_block = self._shared['block']
             block[:SHARED_HEADER].copy_(old_block[:SHARED_HEADER])
-        self._shared_new = dict(base=base.value, opened=opened, block=block)
+        self._shared_new = dict(base=base.value, opened=opened, block=block, nbytes=nbytes)
+        self._fill_peers(base.value, opened)
+        return block[SHARED_HEADER:].view(torch.float64).view(rows, self.ld)
+
+    def _fill_peers(self, base, opened):
         pr = _cabi.Peers(world=self.world, rank=self.rank)
         for q, pq in enumerate(opened):
             pr.Z[q] = pq + SHARED_HEADER
             pr.flags[q] = pq
-        pr.counter = base.value + 2048
-        pr.error = base.value + 1024
+        pr.counter = base + 2048
+        pr.error = base + 1024
         pr.gflag_stride = GFLAG_STRIDE
         self.peers = pr
-        return block[SHARED_HEADER:].view(torch.float64).view(rows, self.ld)
 
     def _finish_shared(self):
         """Second half of a (re)allocation of the shared archive: every rank's block is filled, then the old
@@ -392,14 +436,20 @@ class DreamEngine:
         self.lib.dreamzs_shared_free(C.c_void_p(self._shared['base']))
         self._shared = None
 
-    def close(self):
-        """Collective: unmap the peers' archives and free the shared block (no-op for private archives)."""
+    def close(self, cache=True):
+        """Collective: give the shared archive block back (kept mapped for the next engine of this process group unless
+        cache=False: then the peers' archives are unmapped and the block is freed).  No-op for private archives."""
         if self._shared is not None:
             torch.cuda.synchronize(self.device)
             torch.distributed.barrier(self.group)
             self.Z = None
             self.peers = None
-            self._release_shared()
+            key = (id(self.group), self.device.index)
+            if cache and key not in _SHARED_CACHE:
+                _SHARED_CACHE[key] = dict(self._shared, group=self.group, device=self.device, rank=self.rank, world=self.world)
+                self._shared = None
+            else:
+                self._release_shared()
 
     def rewind(self):
         """Collective.  Forget the rows appended so far (the archive is back to its seed rows) and restart the iteration

@@ -1,6 +1,6 @@
 import os, sys, time
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 local = int(os.environ['LOCAL_RANK']); torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device('cuda', local))
