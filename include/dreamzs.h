@@ -225,15 +225,21 @@ int dreamzs_pt_swap(const dreamzs_config *cfg, const dreamzs_state *st, const dr
  *   dreamzs_accept  : Metropolis accept, state / trace / decision updates, archive append when
  *                     iter % history_thin == 0 (Dream.py:326-362).
  * With multitry = k > 1 (Dream.py:275-323) a chain has 2k-1 points: proposals[nchains_local x (2k-1) x ld],
- * loglike[nchains_local x (2k-1)], aux[nchains_local x (4k+2)], and the iteration is
- *   dreamzs_propose -> caller fills loglike[:, 0:k] -> dreamzs_select (mt_choose_proposal_pt, then the k-1 reference
- *   points around the selected proposal go to proposals[:, k:2k-1]) -> caller fills loglike[:, k:2k-1] ->
- *   dreamzs_accept.  The regenerate loop for a batch without any finite log-posterior (Dream.py:282-289) would need
- *   new draws and is not split: dreamzs_select sets *error (device int32) to 1 instead.
+ * loglike[nchains_local x (2k-1)], aux[nchains_local x (4k+4)], and the iteration is
+ *   dreamzs_propose -> caller fills loglike[:, 0:k] -> [dreamzs_repropose -> caller fills loglike[:, 0:k]]* ->
+ *   dreamzs_select (mt_choose_proposal_pt, then the k-1 reference points around the selected proposal go to
+ *   proposals[:, k:2k-1]) -> caller fills loglike[:, k:2k-1] -> dreamzs_accept.
+ *   dreamzs_repropose is the regenerate loop of Dream.py:278-289: every chain whose k proposals all have a non-finite
+ *   log-posterior draws its next batch (the stream goes on where the previous batch left it) into proposals[:, 0:k];
+ *   *count (device int32, zeroed by the caller) receives the number of such chains -- repeat until it stays 0 (the
+ *   reference has no bound on the loop; the fused kernels stop after 1000 batches).  dreamzs_select sets *error
+ *   (device int32) to 1 for a chain that still has no finite proposal.
  * The random stream resumes in each phase where the previous one left it, so the phases consume exactly the draws
  * of the fused step.  dreamzs_init_logp sets last_prior and leaves last_like = 0 for the caller to fill. */
 int dreamzs_propose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
                     double *proposals, double *aux, void *stream);
+int dreamzs_repropose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
+                      double *proposals, double *aux, const double *loglike, int32_t *count, void *stream);
 int dreamzs_select(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
                    double *proposals, double *aux, const double *loglike, int32_t *error, void *stream);
 int dreamzs_accept(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter,

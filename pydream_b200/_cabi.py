@@ -24,7 +24,7 @@ EXPORTS = ['dreamzs_abi_version', 'dreamzs_init_logp', 'dreamzs_step', 'dreamzs_
            'dreamzs_shared_alloc', 'dreamzs_shared_open', 'dreamzs_shared_close', 'dreamzs_shared_free', 'dreamzs_adapt_workspace_bytes',
            'dreamzs_adapt_colsum', 'dreamzs_adapt_colsq', 'dreamzs_adapt_jumps', 'dreamzs_adapt_finish',
            'dreamzs_gr_chain_stats', 'dreamzs_gr_finish', 'dreamzs_whiten_doubles', 'dreamzs_rng_normals',
-           'dreamzs_debug_set_phase_buffer', 'dreamzs_draw_ws_bytes']
+           'dreamzs_debug_set_phase_buffer', 'dreamzs_draw_ws_bytes', 'dreamzs_repropose']
 
 
 class Config(C.Structure):
@@ -103,6 +103,7 @@ def load():
         'dreamzs_copy_d2h_2d': (C.c_int, [vp, i64, vp, i64, i64, i64, vp]),
         'dreamzs_propose': (C.c_int, [cfgp, stp, i64, i64, vp, vp, vp]),
         'dreamzs_select': (C.c_int, [cfgp, stp, i64, i64, vp, vp, vp, vp, vp]),
+        'dreamzs_repropose': (C.c_int, [cfgp, stp, i64, i64, vp, vp, vp, vp, vp]),
         'dreamzs_accept': (C.c_int, [cfgp, stp, trp, i64, i64, vp, vp, vp, vp]),
         'dreamzs_step_tempered': (C.c_int, [cfgp, stp, trp, i64, i64, vp, vp]),
         'dreamzs_pt_swap': (C.c_int, [cfgp, stp, trp, i64, vp, vp, vp]),

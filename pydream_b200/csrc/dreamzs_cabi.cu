@@ -471,6 +471,19 @@ extern "C" int dreamzs_select(const dreamzs_config *cfg, const dreamzs_state *st
   return dispatch(P, (cudaStream_t)stream);
 }
 
+extern "C" int dreamzs_repropose(const dreamzs_config *cfg, const dreamzs_state *st, int64_t iter, int64_t archive_rows,
+                                 double *proposals, double *aux, const double *loglike, int32_t *count, void *stream) {
+  int rc = ext_common(cfg, st, iter, archive_rows, proposals, aux);
+  if (rc != DREAMZS_OK) return rc;
+  if (cfg->multitry < 2 || !loglike || !count) return DREAMZS_E_BADARG;
+  if (cfg->nchains_local == 0) return DREAMZS_OK;
+  StepParams P{};
+  P.cfg = *cfg; P.st = *st; P.iter_begin = iter; P.niter = 1; P.archive_rows = archive_rows;
+  P.all_flat = all_flat_hint(cfg);
+  P.ext_phase = 4; P.ext_prop = proposals; P.ext_aux = aux; P.ext_like = loglike; P.ext_error = count;
+  return dispatch(P, (cudaStream_t)stream);
+}
+
 extern "C" int dreamzs_accept(const dreamzs_config *cfg, const dreamzs_state *st, const dreamzs_trace *tr, int64_t iter,
                               int64_t archive_rows, const double *proposals, const double *aux, const double *loglike,
                               void *stream) {

@@ -304,9 +304,11 @@ __device__ __forceinline__ void mt_commit(const Ctx<G, 1> &c, const StepParams &
 template <int G>
 __global__ void __launch_bounds__(128, DZ_MTP_MINBLOCKS) dreamzs_mtp_kernel(const __grid_constant__ StepParams P) {
   DZ_MT_PROLOGUE();
+  if (P.peer_error && *reinterpret_cast<volatile int32_t *>(P.peer_error) != 0) return;   // an earlier wait timed out: the host raises
   if (P.wait_k) {   // sharded archive: the peers' rows of the previous append must have landed in this replica
-    if (lane == 0) peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);
-    __syncwarp();
+    int ok = 1;
+    if (lane == 0) ok = peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error) ? 1 : 0;
+    if (!__shfl_sync(0xffffffffu, ok, 0)) return;   // timed out: states stay as they are
   }
 #pragma unroll 1
   for (int it = 0; it < P.niter; ++it) {
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(256, 4) dreamzs_mtdraw_kernel(const __grid_con
     if (tid == 0) peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);
     __syncthreads();
   }
+  if (P.peer_error && *reinterpret_cast<volatile int32_t *>(P.peer_error) != 0) return;   // timed out (now or earlier): the chain kernel leaves too
   const int lane = tid & 31, g = lane & (G - 1);
   Ctx<G, 1> c{P, nullptr, nullptr, nullptr, G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1))), g, d, ld};
   const int i0 = 4 * g;
@@ -478,6 +481,7 @@ __device__ __forceinline__ void mt2_batch(const Ctx<G, 1> &c, Stream &s, bool ru
 template <int G>
 __global__ void __launch_bounds__(128, DZ_MTP_MINBLOCKS) dreamzs_mtchain_kernel(const __grid_constant__ StepParams P) {
   DZ_MT_PROLOGUE();
+  if (P.peer_error && *reinterpret_cast<volatile int32_t *>(P.peer_error) != 0) return;   // the draw kernel's wait for the peers timed out
   const int k = P.cfg.multitry;
   double *pri = c.scal, *lik = c.scal + DREAMZS_MAX_MULTITRY, *snk = c.scal + 2 * DREAMZS_MAX_MULTITRY;
   double *rpri = pri + k, *rlik = lik + k, *rsnk = snk + k;

@@ -565,9 +565,12 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
   for (int j = 0; j < P.cfg.ngamma; ++j) gp[j] = P.st.gamma_probs[j];
 
   const int64_t M = P.archive_rows;
+  if (P.peer_error && *reinterpret_cast<volatile int32_t *>(P.peer_error) != 0) return;   // an earlier wait timed out: the host raises
   if (P.wait_k) {   // sharded archive: the peers' rows of the previous append must have landed in this replica
-    if (c.g == 0) peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error);
-    __syncwarp(c.gmask);
+    int ok = 1;
+    if (c.g == 0) ok = peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error) ? 1 : 0;
+    ok = __shfl_sync(c.gmask, ok, lane & ~(G - 1));
+    if (!ok) return;   // timed out: nothing is sampled from a replica that may miss rows; states stay as they are
   }
 #pragma unroll 1
   for (int it = 0; it < P.niter; ++it) {
@@ -634,11 +637,12 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
       double *rpri = pri + k, *rlik = lik + k, *rsnk = snk + k;   // MAX_MULTITRY >= 2k is not required: see host check
       // Split step with a caller-evaluated likelihood (ext_phase 1 / 2 / 3 = propose / select / accept): the
       // 2k-1 points live in ext_prop [chain][2k-1][ld] (proposals first, then the reference set), their
-      // log-likelihoods in ext_like [chain][2k-1], and the scalars the next phase needs in ext_aux [chain][4k+2]:
+      // log-likelihoods in ext_like [chain][2k-1], and the scalars the next phase needs in ext_aux [chain][4k+4]:
       //   [0,k) log prior, [k,2k) snooker logp of the proposals, 2k: rand() calls made so far, 2k+1: selected index,
-      //   [2k+2,3k+1) / [3k+1,4k) the same of the reference points, 4k: rand() calls, 4k+1: gamma == 1 flag
+      //   [2k+2,3k+1) / [3k+1,4k) the same of the reference points, 4k: rand() calls, 4k+1: gamma == 1 flag,
+      //   4k+2: proposal batches regenerated so far (phase 4 = dreamzs_repropose, the loop of Dream.py:278-289)
       const int npts = 2 * k - 1;
-      double *ax = P.ext_phase ? P.ext_aux + (size_t)c_local * (4 * k + 2) : nullptr;
+      double *ax = P.ext_phase ? P.ext_aux + (size_t)c_local * (4 * k + 4) : nullptr;
       double *xprop = P.ext_phase ? P.ext_prop + (size_t)c_local * npts * ld : nullptr;
       const double *xlike = P.ext_phase >= 2 ? P.ext_like + (size_t)c_local * npts : nullptr;
       if (P.ext_phase <= 1) {
@@ -657,6 +661,7 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
           if (c.g == 0) {
             for (int p = 0; p < k; ++p) { ax[p] = pri[p]; ax[k + p] = snk[p]; }
             ax[2 * k] = (double)s.n_rand;
+            ax[4 * k + 2] = 0.0;
           }
           return;
         }
@@ -664,13 +669,27 @@ __global__ void __launch_bounds__(128) dreamzs_step_kernel(const StepParams P) {
         if (c.g == 0)
           for (int p = 0; p < k; ++p) { pri[p] = ax[p]; snk[p] = ax[k + p]; lik[p] = xlike[p]; }
         __syncwarp(c.gmask);
-        advance_batch_counters(s, dc, k);
+        const int rounds = (int)ax[4 * k + 2];          // batches regenerated so far: each consumed a batch's draws
+        for (int r = 0; r <= rounds; ++r) advance_batch_counters(s, dc, k);
         s.n_rand = (uint32_t)ax[2 * k];
-        if (P.ext_phase == 2) {   // the regenerate loop of Dream.py:282-289 needs new draws: not available in the split step
-          bool anyfinite = false;
-          for (int p = 0; p < k; ++p) anyfinite |= isfinite(Tc * lik[p] + pri[p]);
-          if (!anyfinite && c.g == 0) atomicExch(P.ext_error, 1);
+        bool anyfinite = false;
+        for (int p = 0; p < k; ++p) anyfinite |= isfinite(Tc * lik[p] + pri[p]);
+        if (P.ext_phase == 4) {   // dreamzs_repropose: a chain whose k proposals are all non-finite draws the next batch
+          if (anyfinite) return;
+          gamma_one = gen_eval_batch_mt<G, R>(c, s, dc, k, M, x0, 0, false, pri, lik, snk, D0);
+          for (int p = 0; p < k; ++p) {
+            load_slot<G, R>(c, c.slots + (size_t)p * ld, q);
+            store_row<G, R>(c, xprop + (size_t)p * ld, q);
+          }
+          if (c.g == 0) {
+            for (int p = 0; p < k; ++p) { ax[p] = pri[p]; ax[k + p] = snk[p]; }
+            ax[2 * k] = (double)s.n_rand;
+            ax[4 * k + 2] = (double)(rounds + 1);
+            atomicAdd(P.ext_error, 1);              // (here: the number of chains that drew a new batch)
+          }
+          return;
         }
+        if (P.ext_phase == 2 && !anyfinite && c.g == 0) atomicExch(P.ext_error, 1);   // the caller gave up regenerating
       }
       if (P.ext_phase <= 2) {
         // mt_choose_proposal_pt, Dream.py:883-917

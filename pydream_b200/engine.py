@@ -274,7 +274,7 @@ class DreamEngine:
             k = int(multitry)
             self._mt = k
             self._prop = torch.zeros((self.Nl, 2 * k - 1, self.ld), **f64)     # proposals, then the reference set
-            self._aux = torch.zeros((self.Nl, 4 if k == 1 else 4 * k + 2), **f64)
+            self._aux = torch.zeros((self.Nl, 4 if k == 1 else 4 * k + 4), **f64)
             self._like = torch.zeros((self.Nl, 2 * k - 1), **f64)
             self._ext_error = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.last_like.copy_(target.evaluate(self.X[:, :d].contiguous()))     # first-call logp, Dream.py:266-268
@@ -470,14 +470,16 @@ class DreamEngine:
 
     def check_peers(self):
         """Raise if a wait for a peer's append timed out (DREAMZS_PEER_TIMEOUT_NS), or if a multi-try batch of the split
-        step had no finite log-posterior (the reference would redraw it, Dream.py:282-289)."""
+        step still had no finite log-posterior after 1000 regenerated batches (Dream.py:278-289 would loop on)."""
         if self.external and int(self._ext_error.item()) != 0:
-            raise _cabi.DreamzsError('every proposal of a multi-try batch had a non-finite log-posterior: the split step '
-                                     'cannot redraw it')
+            raise _cabi.DreamzsError('every proposal of a multi-try batch had a non-finite log-posterior, 1000 regenerated '
+                                     'batches included')
         if self._shared is not None:
             err = self._shared['block'][1024:1028].view(torch.int32)
             if int(err.item()) != 0:
                 raise _cabi.DreamzsError('timed out waiting for a peer GPU to publish its archive append')
+        if self.sync_ws is not None and self.persistent and int(self.sync_ws[0].item()) != 0:
+            raise _cabi.DreamzsError('a persistent launch gave up waiting for rows appended inside it (abort word set)')
 
     @property
     def archive_rows(self):
@@ -552,6 +554,14 @@ class DreamEngine:
             _cabi.check(lib.dreamzs_propose(cfg, st, t, self.archive_rows, p(self._prop), p(self._aux), stream), 'dreamzs_propose')
             self._like[:, :k] = self.target.evaluate(self._prop[:, :k, :d].reshape(-1, d).contiguous()).view(self.Nl, k)
             if k > 1:      # multi-try: pick a proposal, then the reference set around it (Dream.py:291-303)
+                for _ in range(1000):    # Dream.py:278-289: chains without any finite proposal draw the next batch
+                    self._ext_error.zero_()
+                    _cabi.check(lib.dreamzs_repropose(cfg, st, t, self.archive_rows, p(self._prop), p(self._aux), p(self._like),
+                                                      p(self._ext_error), stream), 'dreamzs_repropose')
+                    self.launches += 1
+                    if int(self._ext_error.item()) == 0:
+                        break
+                    self._like[:, :k] = self.target.evaluate(self._prop[:, :k, :d].reshape(-1, d).contiguous()).view(self.Nl, k)
                 _cabi.check(lib.dreamzs_select(cfg, st, t, self.archive_rows, p(self._prop), p(self._aux), p(self._like),
                                                p(self._ext_error), stream), 'dreamzs_select')
                 self._like[:, k:] = self.target.evaluate(self._prop[:, k:, :d].reshape(-1, d).contiguous()).view(self.Nl, k - 1)

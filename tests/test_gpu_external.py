@@ -143,3 +143,31 @@ def test_external_multitry_bounded_prior():
         assert np.all(np.abs(l[c][:, 0] - orc['logp'][:, c]) <= logp_tol(orc['logp'][:, c]))
         np.testing.assert_allclose(s[c], ref_s[c], rtol=1e-12)
         np.testing.assert_allclose(l[c], ref_l[c], rtol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['const4_mt3_regen', 'sum10_mt5_regen'])
+def test_external_multitry_regenerates_batches(name):
+    """Uniform priors without hard boundaries: whole proposal batches fall outside the support (log prior -inf) and are
+    regenerated (Dream.py:278-289) -- in the split step by dreamzs_repropose between the caller's evaluations."""
+    import torch
+    from oracle import c_oracle
+    from pydream_b200.engine import DreamEngine
+    from test_gpu_multitry import CASES, _case
+    case = [c for c in CASES if c[0] == name][0]
+    _, d, N, T, tgt, (pk, pa, pb), kw, hist = _case(case)
+    kw = dict(kw, adapt_crossover=False)
+    ref = c_oracle.OracleSampler(d, N, hist, hist[:N].copy(), tgt.kind, tgt.table(), seed=77, prior_kind=pk, prior_a=pa,
+                                 prior_b=pb, **kw).run(T, rows_dbg_n=96)
+    k, snk = kw['multitry'], (ref['decisions'] >> 1) & 1
+    normal = np.where(snk == 1, 3 * (2 * k - 1), 2 * kw.get('DEpairs', 1) * (2 * k - 1))
+    assert int(((ref['rows'] >= 0).sum(axis=2) > normal).sum()) > 0            # batches were in fact regenerated
+    fn = (lambda x: torch.zeros(x.shape[0], dtype=torch.float64, device=x.device)) if name.startswith('const') \
+        else (lambda x: (x + 3.0).sum(dim=1))
+    eng = DreamEngine(d, N, hist, hist[:N].copy(), targets.TorchLikelihood(d, fn), pk, pa, pb, seed=77, **kw)
+    got = _run(eng, T)
+    eng.check_peers()
+    np.testing.assert_array_equal(got[2], ref['decisions'])
+    fin = np.isfinite(ref['logp'])
+    assert np.array_equal(fin, np.isfinite(got[1]))
+    assert np.all(np.abs(got[1][fin] - ref['logp'][fin]) <= 10 * logp_tol(ref['logp'][fin]))
+    np.testing.assert_allclose(got[0], ref['states'], rtol=1e-10, atol=1e-11)
