@@ -114,8 +114,12 @@ __device__ __forceinline__ uint4 philox_inl(uint32_t c0, uint32_t c1, uint32_t c
 // bound by dependent latency and the fp64 pipe is idle there).  With A = ones, D = A B sums the B fragment's columns:
 // lane l gets the sums of lanes {8m..8m+3} and {8m+4..8m+7}, m = l % 4; their sum T[m] goes through a second product
 // whose A fragment selects the T's of the lane's own chain.  Every lane of a chain ends with the same bits.
+template <int LPC> __device__ __forceinline__ double lsum(double v);
 template <int LPC>
 __device__ __forceinline__ double lsum_mma(double v, double a2) {
+#ifdef DZ_WW_SHFL_SUM   // A/B: butterfly of shuffles instead
+  return lsum<LPC>(v);
+#endif
   double d0 = 0.0, d1 = 0.0;
   dmma884(d0, d1, 1.0, v);
   const double t = d0 + d1;
@@ -134,6 +138,11 @@ __device__ __forceinline__ double lsum(double v) {
 #pragma unroll
   for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// the row is on its way from HBM to L2 (sm_90+ bulk prefetch): issued a batch ahead of the TMA copy that stages it
+__device__ __forceinline__ void l2_prefetch_row(const double *row, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
@@ -487,6 +496,7 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
         if (rb >= ra) rb += 1;
         rows[3 * col] = ra; rows[3 * col + 1] = rb; rows[3 * col + 2] = -1;
         if (row_maybe_late(rw, known, ra) || row_maybe_late(rw, known, rb)) mt |= 4096u;
+        else { l2_prefetch_row(P.st.Z + (size_t)ra * ld, row_bytes); l2_prefetch_row(P.st.Z + (size_t)rb * ld, row_bytes); }
         dpr[col] = 0;
         gsn[col] = ((double)(q1.x + 1u) / (double)P.cfg.nCR) * 4294967296.0;   // DE column: CR 2^32 for the crossover test
       } else {
@@ -497,6 +507,10 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
         const int64_t r1 = (int64_t)(((uint64_t)r7.x * (uint64_t)w.M) >> 32), r2 = (int64_t)(((uint64_t)r8.x * (uint64_t)w.M) >> 32);
         rows[3 * col] = rz; rows[3 * col + 1] = r1; rows[3 * col + 2] = r2;
         if (row_maybe_late(rw, known, rz) || row_maybe_late(rw, known, r1) || row_maybe_late(rw, known, r2)) mt |= 4096u;
+        else {
+          l2_prefetch_row(P.st.Z + (size_t)rz * ld, row_bytes); l2_prefetch_row(P.st.Z + (size_t)r1 * ld, row_bytes);
+          l2_prefetch_row(P.st.Z + (size_t)r2 * ld, row_bytes);
+        }
         const int slot = atomicAdd(pool_n, 1);                               // z1 - z2 goes to the pool when a slot is left
         dpr[col] = slot < L.npool ? slot : -1;
       }
