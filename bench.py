@@ -57,7 +57,7 @@ WORKLOADS = {
                seed_dist='normal', kernel='dreamzs_mtchain_kernel<4> (after dreamzs_mtdraw_scalars_kernel + dreamzs_mtdraw_kernel<4>, three launches per window)'),
     'c4': dict(label='C4: 200-D twisted Gaussian (banana, b=0.1), 8192 chains in total', d=200, chains=8192,
                scaling='strong', target='banana', nseed=131072, iters_per_step=100, opts=dict(COMMON, multitry=1),
-               seed_dist='banana', kernel='dreamzs_step_kernel<32,2,false>'),
+               seed_dist='banana', kernel='dreamzs_stdraw_kernel<32,2> + dreamzs_stchain_kernel<32,2> (two launches per window)'),
     'c5': dict(label='C5: 50-D correlated Gaussian, 65536 chains in total, steady-state step (crossover adaptation during '
                      'burn-in and Gelman-Rubin timed separately: burnin / rhat)', d=50, chains=65536, scaling='strong',
                target='gaussian', nseed=524288, iters_per_step=20, opts=dict(COMMON, multitry=1), seed_dist='box',

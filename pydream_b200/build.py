@@ -65,6 +65,9 @@ def build(force=False, verbose=False):
     for tc in GWIN_VARIANTS:
         jobs.append((os.path.join(CSRC, 'dreamzs_gwin_inst.cu'), os.path.join(OBJ, 'gwin_%d.o' % tc),
                      ['-DDZ_TC=%d' % tc], hdr_mtime, force))
+    for g, r in STEP_VARIANTS:
+        jobs.append((os.path.join(CSRC, 'dreamzs_st2_inst.cu'), os.path.join(OBJ, 'st2_%d_%d.o' % (g, r)),
+                     ['-DDZ_G=%d' % g, '-DDZ_R=%d' % r], hdr_mtime, force))
     for g in MTP_VARIANTS:
         jobs.append((os.path.join(CSRC, 'dreamzs_mtp_inst.cu'), os.path.join(OBJ, 'mtp_%d.o' % g),
                      ['-DDZ_G=%d' % g], hdr_mtime, force))

@@ -1,12 +1,14 @@
 // extern "C" entry points of libdreamzs.so for the fused step (include/dreamzs.h) and the
 // dispatch over the <G, R> kernel instantiations (one object file each, dreamzs_step_inst.cu).
+#include <stdlib.h>
 #include <string.h>
 #include "dreamzs_step_params.cuh"
 #include "dreamzs_common.cuh"
 
 using namespace dreamzs;
 
-#define DZ_DECL(g, r) int dreamzs_launch_step_##g##_##r(const dreamzs::StepParams &, int, size_t, cudaStream_t);
+#define DZ_DECL(g, r) int dreamzs_launch_step_##g##_##r(const dreamzs::StepParams &, int, size_t, cudaStream_t); \
+  int dreamzs_launch_st2_##g##_##r(const dreamzs::StepParams &, int, size_t, cudaStream_t);
 DZ_DECL(4, 1) DZ_DECL(8, 1) DZ_DECL(16, 1) DZ_DECL(32, 1) DZ_DECL(32, 2) DZ_DECL(32, 4) DZ_DECL(32, 8)
 #undef DZ_DECL
 int dreamzs_launch_mtp_4(const dreamzs::StepParams &, size_t, cudaStream_t);
@@ -89,10 +91,27 @@ static bool mtp_eligible(const StepParams &P) {
          !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL);
 }
 
+// two-stage single-try step (dreamzs_st2_kernel.cuh): bytes of one iteration's records, and how many iterations' worth to
+// keep.  Measured at C4 (26.5 MB per iteration): sub-spans of 2 iterations, whose records stay in L2, 209 M chain-steps/s;
+// the whole window of 10 in one draw + chain pair (265 MB through HBM) 264 M -- launches cost more than the traffic
+static int64_t st2_iter_bytes(const dreamzs_config &cfg) { return (int64_t)cfg.nchains_local * (4 + 2 * cfg.ld) * (int64_t)sizeof(double); }
+static int64_t st2_budget() {      // DREAMZS_ST2_BUDGET_MB: experiments
+  static const int64_t v = [] { const char *e = getenv("DREAMZS_ST2_BUDGET_MB"); return (int64_t)(e ? atoi(e) : 1024) << 20; }();
+  return v;
+}
+
 extern "C" int64_t dreamzs_draw_ws_bytes(const dreamzs_config *cfg, int32_t niter) {
-  if (!cfg || niter < 1) return 0;
+  if (!cfg || niter < 1 || cfg->nchains_local < 1) return 0;
   StepParams P{};
   P.cfg = *cfg;
+  if (cfg->multitry == 1) {
+    if (cfg->target_kind == DREAMZS_TARGET_EXTERNAL || (cfg->flags & DREAMZS_FLAG_GENERIC_KERNEL)) return 0;
+    const int64_t per = st2_iter_bytes(*cfg);
+    int64_t nb = st2_budget() / per;
+    if (nb < 1) nb = 1;
+    if (nb > niter) nb = niter;
+    return nb * per;
+  }
   if (!mtp_eligible(P)) return 0;
   return (int64_t)cfg->nchains_local * niter * (8 + (2 * cfg->multitry - 1) * 2 * cfg->ld) * (int64_t)sizeof(double);
 }
@@ -140,6 +159,18 @@ static int dispatch(StepParams &P, cudaStream_t stream) {
     if (P.st.draw_ws && (P.st.draw_ws_bytes < dreamzs_draw_ws_bytes(&cfg, P.niter))) P.st.draw_ws = nullptr;
     const size_t smem_b = chain_b + (P.table_in_smem ? table_b : 0);
     return G == 4 ? dreamzs_launch_mtp_4(P, smem_b, stream) : dreamzs_launch_mtp_8(P, smem_b, stream);
+  }
+  // single try with scratch for the draws: draw kernel + chain kernel per sub-span of the window (dreamzs_st2_kernel.cuh)
+  if (cfg.multitry == 1 && !P.ext_phase && !P.init_only && P.st.draw_ws && P.st.draw_ws_bytes >= st2_iter_bytes(cfg) &&
+      cfg.target_kind != DREAMZS_TARGET_EXTERNAL && !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL)) {
+    const int cpc = (threads / 32) * (32 / G);
+    const size_t chain_b = (size_t)cpc * cfg.ld * sizeof(double);
+    const size_t table_b = (size_t)((P.table_doubles + 1) & ~1) * sizeof(double);
+    P.table_in_smem = (table_b + chain_b <= 200 * 1024) ? 1 : 0;
+    const size_t smem_b = chain_b + (P.table_in_smem ? table_b : 0);
+#define DZ_CASE(g, r) if (G == g && R == r) return dreamzs_launch_st2_##g##_##r(P, threads, smem_b, stream);
+    DZ_CASE(4, 1) DZ_CASE(8, 1) DZ_CASE(16, 1) DZ_CASE(32, 1) DZ_CASE(32, 2) DZ_CASE(32, 4) DZ_CASE(32, 8)
+#undef DZ_CASE
   }
   const int chains_per_cta = (threads / 32) * (32 / G);
   const size_t chain_bytes = (size_t)chains_per_cta * ((size_t)P.nslots * cfg.ld + 3 * DREAMZS_MAX_MULTITRY) * sizeof(double);
@@ -353,6 +384,15 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
         st->draw_ws_bytes >= dreamzs_draw_ws_bytes(cfg, (int32_t)(thin < niter ? thin : niter)))
       kern_per_window = 3;
   }
+  int st2_nb = 0;    // two-stage single-try step: iterations per (draw, chain) kernel pair, 0 = not in use
+  {
+    StepParams Q{};
+    Q.cfg = *cfg; Q.st = *st; Q.all_flat = all_flat_hint(cfg);
+    if (check_cfg(cfg, st) == DREAMZS_OK && cfg->multitry == 1 && cfg->target_kind != DREAMZS_TARGET_EXTERNAL && st->draw_ws &&
+        st->draw_ws_bytes >= st2_iter_bytes(*cfg) && !(cfg->flags & DREAMZS_FLAG_GENERIC_KERNEL) && !wwin_eligible(Q) &&
+        !gwin_eligible(Q) && !(cfg->target_kind == DREAMZS_TARGET_GAUSSIAN_DENSE && cfg->ld > 64 && cfg->ld <= 128))
+      st2_nb = (int)(st->draw_ws_bytes / st2_iter_bytes(*cfg));
+  }
   while (t < end) {
     const int64_t nxt = ((t + thin - 1) / thin) * thin;          // first appending iteration >= t
     int64_t n = (end < nxt + 1 ? end : nxt + 1) - t;
@@ -383,7 +423,7 @@ extern "C" int dreamzs_run(const dreamzs_config *cfg, const dreamzs_state *st, c
                        (p2p && !waited) ? (uint64_t)appends_done : 0, (p2p && appends) ? (uint64_t)(appends_done + 1) : 0, stream);
     if (rc != DREAMZS_OK) return rc;
     waited = true;
-    nl += kern_per_window;
+    nl += (st2_nb > 0 && !burn) ? 2 * ((n + st2_nb - 1) / st2_nb) : kern_per_window;
     if (appends) {                                               // record_history for every chain (Dream.py:919-938)
       ++appends_done;
       if (p2p) {

@@ -208,14 +208,18 @@ __device__ __forceinline__ const double2 *row_ptr(const double *Z, int64_t row, 
 template <int G, int R>
 __device__ __forceinline__ void de_draw(const Ctx<G, R> &c, Stream &s, const Decisions &dc, const Bases &b, int n,
                                         int p, int64_t M, double (&J)[R][4], double (&zeta)[R][4], unsigned &reset,
-                                        bool &gamma_one) {
+                                        bool &gamma_one, const uint4 *w_sample = nullptr, const double *u_unity = nullptr,
+                                        float (*nzf)[4] = nullptr) {
+  // (w_sample / u_unity: block 0 of the random.sample call and the uniform of the gamma-unity multinomial when the caller
+  // has drawn them already -- the two-stage draw kernel makes all scalar draws of an iteration in one lane-parallel pass;
+  // nzf: also return the float32 normals zeta was made of, zeta = 0.0 + cfg.zeta * (double)nzf)
   const StepParams &P = c.P;
   const int d = c.d, delta = dc.delta;
   const double *Z = P.st.Z;
   // --- archive rows: random.sample(range(M), 2 delta)
   double diff[R][4];
   if (delta == 1) {
-    const uint4 w = s.block(b.s + p, ST_SAMPLE, 0);
+    const uint4 w = w_sample ? *w_sample : s.block(b.s + p, ST_SAMPLE, 0);
     const int64_t r0 = (int64_t)(((uint64_t)w.x * (uint64_t)M) >> 32);
     int64_t r1 = (int64_t)(((uint64_t)w.y * (uint64_t)(M - 1)) >> 32);
     if (r1 >= r0) r1 += 1;
@@ -266,8 +270,10 @@ __device__ __forceinline__ void de_draw(const Ctx<G, R> &c, Stream &s, const Dec
     const uint32_t blk = (uint32_t)(c.g + G * r);
     const int i0 = c.dim0(r);
     if (i0 < d) {
-      double nz[4];
-      normal4(s.block(b.n + p, ST_NORMAL, blk), nz);
+      float nf[4];
+      normal4f(s.block(b.n + p, ST_NORMAL, blk), nf);
+      const double nz[4] = {(double)nf[0], (double)nf[1], (double)nf[2], (double)nf[3]};
+      if (nzf) { nzf[r][0] = nf[0]; nzf[r][1] = nf[1]; nzf[r][2] = nf[2]; nzf[r][3] = nf[3]; }
       const uint4 we = s.block(b.u + p, ST_UNIFORM_VEC, blk);
       const uint4 wu = s.block(b.u + n + p, ST_UNIFORM_VEC, blk);
       const uint32_t wev[4] = {we.x, we.y, we.z, we.w}, wuv[4] = {wu.x, wu.y, wu.z, wu.w};
@@ -283,12 +289,14 @@ __device__ __forceinline__ void de_draw(const Ctx<G, R> &c, Stream &s, const Dec
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { zeta[r][j] = 0.0; e[r][j] = 1.0; }
+      for (int j = 0; j < 4; ++j) { zeta[r][j] = 0.0; e[r][j] = 1.0; if (nzf) nzf[r][j] = 0.0f; }
     }
   }
   dprime = gsum_int<G>(dprime, c.gmask);
   // --- gamma: the unity draw is always made (Dream.py:615)
-  const int unity = multinomial2(s, P.cfg.p_gamma_unity);   // call number advanced by the caller's order
+  int unity;
+  if (u_unity) { unity = (*u_unity < 0.0 + P.cfg.p_gamma_unity) ? 0 : 1; s.n_multinomial++; }
+  else unity = multinomial2(s, P.cfg.p_gamma_unity);   // call number advanced by the caller's order
   double gamma;
   if (unity == 0) gamma = 1.0;
   else {
@@ -324,13 +332,14 @@ __device__ __forceinline__ void de_point(const Ctx<G, R> &c, Stream &s, const De
 // The archive rows of one snooker proposal (Dream.py:802-810): z (the projection anchor) and z1 - z2.
 template <int G, int R>
 __device__ __forceinline__ void snooker_rows(const Ctx<G, R> &c, const Stream &s, const Bases &b, int n, int p, int64_t M,
-                                             double (&z)[R][4], double (&t)[R][4]) {
+                                             double (&z)[R][4], double (&t)[R][4], const uint4 *pre = nullptr) {
   const StepParams &P = c.P;
   const int d = c.d;
   const double *Z = P.st.Z;
-  const uint4 wz = s.block(b.s + p, ST_SAMPLE, 0);
-  const uint4 w1 = s.block(b.s + n + 2 * p, ST_SAMPLE, 0);
-  const uint4 w2 = s.block(b.s + n + 2 * p + 1, ST_SAMPLE, 0);
+  // (pre: the three sample blocks when the caller has drawn them already)
+  const uint4 wz = pre ? pre[0] : s.block(b.s + p, ST_SAMPLE, 0);
+  const uint4 w1 = pre ? pre[1] : s.block(b.s + n + 2 * p, ST_SAMPLE, 0);
+  const uint4 w2 = pre ? pre[2] : s.block(b.s + n + 2 * p + 1, ST_SAMPLE, 0);
   const int64_t rz = (int64_t)(((uint64_t)wz.x * (uint64_t)M) >> 32);
   const int64_t r1 = (int64_t)(((uint64_t)w1.x * (uint64_t)M) >> 32);
   const int64_t r2 = (int64_t)(((uint64_t)w2.x * (uint64_t)M) >> 32);

@@ -174,7 +174,7 @@ class DreamEngine:
                  nCR=3, gamma_levels=1, DEpairs=1, multitry=1, snooker=.1, p_gamma_unity=.2, lamb=.05, zeta=1e-12,
                  history_thin=10, hardboundaries=True, adapt_crossover=False, adapt_gamma=False, crossover_burnin=0,
                  cr_probs=None, gamma_probs=None, device=None, group=None, record_decisions=True,
-                 generic_kernel=False, window_kernel=True, reserve_iters=0, peer_archive=True, whitened=True, persistent=True, two_stage=True):
+                 generic_kernel=False, window_kernel=True, reserve_iters=0, peer_archive=True, whitened=True, persistent=True, two_stage=True, draw_iters=None):
         if not torch.cuda.is_available():
             raise _cabi.DreamzsError('pydream_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _cabi.load()
@@ -258,7 +258,9 @@ class DreamEngine:
                                 | (0 if window_kernel else _cabi.FLAG_NO_WINDOW_KERNEL),
                                 snooker=snooker, p_gamma_unity=p_gamma_unity, lamb=lamb, zeta=zeta, seed=int(seed) & (2 ** 64 - 1))
         # scratch of the two-stage multi-try step (dreamzs_state.draw_ws): every draw of a window, made ahead of the chains
-        nb = int(self.lib.dreamzs_draw_ws_bytes(C.byref(self.cfg), self.thin)) if (two_stage and not self.external) else 0
+        # (the dense-Gaussian window kernels need none)
+        windowed = dense and self.all_flat and DEpairs == 1 and multitry == 1 and window_kernel and not generic_kernel
+        nb = int(self.lib.dreamzs_draw_ws_bytes(C.byref(self.cfg), min(self.thin, int(draw_iters or self.thin)))) if (two_stage and not self.external and not windowed) else 0
         self.draw_ws = torch.empty(nb // 8, **f64) if 0 < nb <= 2 ** 31 else None
         ws = self.lib.dreamzs_adapt_workspace_bytes(C.byref(self.cfg))
         self.workspace = torch.zeros(max(int(ws), 8) // 8 + 1, **f64)

@@ -97,3 +97,37 @@ def test_two_stage_runs_long_windows():
     eng = DreamEngine(d, N, hist, hist[:N].copy(), tgt, seed=3, **kw)
     trace, logp, dec = eng.run(T)
     assert np.array_equal(dec.t().contiguous().cpu().numpy().astype(np.uint32), ref['decisions'])
+
+
+# ---------------------------------------------------------------- two-stage single-try step (dreamzs_st2_kernel.cuh)
+ST_CASES = [
+    ('banana200', 200, 64, 24, 'banana', dict(kind='flat'), dict(snooker=.1, history_thin=6)),
+    ('banana530_r8', 530, 20, 10, 'banana', dict(kind='flat'), dict(snooker=.3, history_thin=2)),
+    ('mix10_pairs3', 10, 60, 30, 'mixture', dict(kind='flat'), dict(snooker=.2, history_thin=5, DEpairs=3, gamma_levels=2)),
+    ('sum6_bounds', 6, 80, 40, 'sumshift', dict(kind='uniform', loc=[-.5] * 6, scale=[1.] * 6), dict(snooker=.2, history_thin=5, zeta=1e-3, lamb=.4)),
+    ('norm5', 5, 40, 30, 'sumshift', dict(kind='norm', loc=[.3] * 5, scale=[2.] * 5), dict(snooker=.1, history_thin=4)),
+    ('gauss40_norm', 40, 40, 20, 'gaussian', dict(kind='norm', loc=[5.] * 40, scale=[10.] * 40), dict(snooker=.1, history_thin=5)),
+]
+
+
+@pytest.mark.parametrize('draw_iters', [None, 2])
+@pytest.mark.parametrize('case', ST_CASES, ids=[c[0] for c in ST_CASES])
+def test_two_stage_single_try_matches_c_oracle(case, draw_iters):
+    """draw kernel + chain kernel per sub-span of a window (draw_iters=2: windows cut into sub-spans of two iterations)."""
+    from oracle import c_oracle
+    from pydream_b200.engine import DreamEngine
+    name, d, N, T, tgt, (pk, pa, pb), kw, hist = _case(tuple(case[:6]) + (dict(case[6], multitry=1),))
+    kw = dict(kw, adapt_crossover=False)
+    ref = c_oracle.OracleSampler(d, N, hist, hist[:N].copy(), tgt.kind, tgt.table(), seed=78, prior_kind=pk, prior_a=pa,
+                                 prior_b=pb, **kw).run(T)
+    eng = DreamEngine(d, N, hist, hist[:N].copy(), tgt, pk, pa, pb, seed=78, draw_iters=draw_iters, **kw)
+    assert eng.draw_ws is not None
+    launches0 = eng.launches
+    trace, logp, dec = eng.run(T)
+    assert eng.launches - launches0 > T // kw['history_thin']          # more than one kernel per window: the two-stage form ran
+    got_dec = dec.t().contiguous().cpu().numpy().astype(np.uint32)
+    got_lp = logp.t().contiguous().cpu().numpy()
+    got_sp = trace[:, :, :d].permute(1, 0, 2).contiguous().cpu().numpy()
+    assert np.array_equal(got_dec, ref['decisions']), 'decisions differ at %s' % (np.argwhere(got_dec != ref['decisions'])[:3].tolist(),)
+    assert np.all(np.abs(got_lp - ref['logp']) <= 10 * logp_tol(ref['logp'])), (np.abs(got_lp - ref['logp']) / logp_tol(ref['logp'])).max()
+    np.testing.assert_allclose(got_sp, ref['states'], rtol=1e-10, atol=1e-11)

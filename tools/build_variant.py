@@ -18,6 +18,22 @@ def main():
     B.build()
     out = os.path.join(ROOT, 'build', 'variants')
     os.makedirs(out, exist_ok=True)
+    if any(x.startswith('-DDZ_ST2') for x in defs):     # variants of the two-stage single-try kernels
+        objs = [os.path.join(B.OBJ, f) for f in sorted(os.listdir(B.OBJ)) if f.endswith('.o') and not f.startswith('st2_')]
+        mine = []
+        for g, r in B.STEP_VARIANTS:
+            o = os.path.join(out, '%s_st2_%d_%d.o' % (name, g, r))
+            cmd = [B._nvcc()] + B.NVCC_FLAGS + ['-DDZ_G=%d' % g, '-DDZ_R=%d' % r] + defs + ['-c', os.path.join(B.CSRC, 'dreamzs_st2_inst.cu'), '-o', o]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            if p.returncode != 0:
+                raise SystemExit(p.stdout + p.stderr)
+            mine.append(o)
+        lib = os.path.join(out, 'libdreamzs_%s.so' % name)
+        subprocess.check_call([B._nvcc(), '-shared', '-o', lib] + objs + mine + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+        for o in mine:
+            os.remove(o)
+        print(lib)
+        return
     if any(x.startswith('-DDZ_MTP') for x in defs):     # variants of the point-parallel multi-try kernel
         objs = [os.path.join(B.OBJ, f) for f in sorted(os.listdir(B.OBJ)) if f.endswith('.o') and not f.startswith('mtp_')]
         mine = []
