@@ -2,9 +2,10 @@
 
 Replaces, for analytic targets, the reference's process pool + shared-memory namespace
 (pydream/core.py:66-129, 250-327; pydream/Dream_shared_vars.py): every chain is a lane-group of
-one fused kernel, the archive ``Z`` lives in HBM, and the chain loop of ``_sample_dream`` becomes
-a sequence of launches of up to ``history_thin`` fused iterations (the archive is immutable inside
-such a window).  PyTorch is used only for device memory, streams and ``torch.distributed``.
+a step kernel, the archive ``Z`` lives in HBM, and the chain loop of ``_sample_dream`` becomes the native
+loop ``dreamzs_run``: one persistent launch per span of windows for the dense Gaussian (whitened window kernel),
+otherwise one launch -- or a draw kernel + a chain kernel -- per window of up to ``history_thin`` iterations (the
+archive is immutable inside a window).  PyTorch is used only for device memory, streams and ``torch.distributed``.
 
 Data layout in HBM (all float64, row stride ``ld`` = ndim rounded up to 4 doubles = 32 B):
     Z      [capacity_rows, ld]   archive, seed rows first, then N rows per append in chain order
@@ -12,10 +13,11 @@ Data layout in HBM (all float64, row stride ``ld`` = ndim rounded up to 4 double
     trace  [N_local, T, ld]      sampled_params (chain-major: chain c's trace is contiguous)
     logp   [N_local, T]          log_ps
     dec    [N_local, T] uint32   decision words (accept / snooker / CR / gamma level / multi-try pick)
-Sharding: rank r owns global chains [r*N/G, (r+1)*N/G); Z is replicated on every GPU.  The appending iteration of
-a launch stores each new row into ALL replicas (peer stores over NVLink from inside the step kernel, system-scope
-flags; `dreamzs_peers`); when the ranks cannot map each other's memory the rows are all-gathered in place with
-NCCL after every appending launch instead.
+Sharding: rank r owns global chains [r*N/G, (r+1)*N/G); Z is replicated on every GPU.  An appending iteration
+stores each new row into ALL replicas (peer stores over NVLink from inside the step kernel; blocks confirmed by
+system-scope flags, rows of not yet confirmed blocks read from the owner's archive: `dreamzs_peers`, DESIGN.md
+section 6); only when the ranks cannot map each other's memory are the rows all-gathered in place with NCCL after
+every appending launch instead.
 """
 import ctypes as C
 import math
