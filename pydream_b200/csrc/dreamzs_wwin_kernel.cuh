@@ -846,11 +846,13 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
             // |prop - z|^2 and Q' together
             nn = lsum_mma<LPC>(nn, a2sel);
             part = lsum_mma<LPC>(part, a2sel);
-            if (run_snooker) {
-              const double norm = sqrt(nn);
-              snk_logp = (norm != 0 ? log(norm) : 0.0) * (d - 1);
-              const double n0 = sqrt(D);
-              cur = (n0 != 0 ? log(n0) : 0.0) * (d - 1);
+            {
+              // log |prop - z| and log |x - z| (Dream.py:326-332, 834-835) in ONE sqrt + log pass: even lanes take the first,
+              // odd lanes the second (a warp instruction costs the same for one lane as for 32), then neighbours swap
+              const double nrm = sqrt((lane & 1) ? D : nn);
+              const double lg = (nrm != 0 ? log(nrm) : 0.0) * (d - 1);
+              const double lo = __shfl_xor_sync(0xffffffffu, lg, 1);
+              if (run_snooker) { snk_logp = (lane & 1) ? lo : lg; cur = (lane & 1) ? lg : lo; }
             }
           } else {
             part = fma(un[1], un[1], un[0] * un[0]) + fma(un[3], un[3], un[2] * un[2]);
