@@ -338,7 +338,6 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
   double *pool = reinterpret_cast<double *>(smem_raw + L.oPool);
   int *pool_n = reinterpret_cast<int *>(probs + 34);          // snooker columns of the batch that hold a pool slot
   int *known = reinterpret_cast<int *>(probs + 35);           // [1 + DREAMZS_MAX_PEERS] append blocks known complete (row_ready)
-  int *fwd_cnt = reinterpret_cast<int *>(probs + 44);         // chains of the group whose appended row is in the archive (peer forwarding)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double logF = P.st.target_table[0];
   int dbg_n = 0;
@@ -897,26 +896,13 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
                 }
             }
           }
-          if (appending && (counters || P.publish_k)) {
-            // the row is visible before the chain counts itself: to this GPU (multi-window launch: local readers watch the
-            // counter), to the peers as well when the chain's warp stores the replicas itself
-            // the row is visible on this GPU before the chain counts itself.  Several windows per launch: no system-scope
-            // fence here (~14 us on B200, and every chain of the window would pay it before the CTA's next barrier): the
-            // peers read a block from their replica only after the confirmer has confirmed it, from this archive before.
-            if (!counters && P.npeers) __threadfence_system(); else __threadfence();
+          if (appending && !counters && P.publish_k) {
+            // one launch per window on several GPUs: the chain's warp has stored the replicas itself; the rows are visible
+            // system-wide before the chain counts itself.  (Several windows per launch: no fence on the chains' path at all --
+            // one thread publishes the group's append after the batch, see below.)
+            __threadfence_system();
             __syncwarp();
-            if (g == 0 && valid) {
-              if (counters) {
-                if (P.ww_gdone) atomicAdd(P.ww_gdone + it.grp, 1u);
-                if (P.my_pub && atomicAdd(fwd_cnt, 1) == nch_cta - 1) {   // last chain of the group: its progress word
-                  atomicExch(fwd_cnt, 0);
-                  __threadfence();
-                  *reinterpret_cast<volatile uint64_t *>(P.my_pub + it.grp) = P.ww_k0 + (uint64_t)blk + 1u;
-                }
-                atomicAdd(counters + blk, 1u);   // (the confirmer CTA watches this one)
-              }
-              else peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
-            }
+            if (g == 0 && valid) peer_chain_appended(P.peer_counter, (unsigned)P.cfg.nchains_local, P.peer_flag, P.npeers, P.publish_k);
           }
           if (g == 0 && valid) {
             *lrow_ptr = last_like + last_prior;
@@ -941,6 +927,16 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
     WW_STAMP();   // +5: chains advanced
     const long long tp3 = (P.dbg && tid == 0) ? clock64() : 0;
     __syncthreads();   // the slots are free for the next batch; parked states and the next batch's draws are visible
+    if (counters && w_append && it.last_batch && tid == WW_THREADS - 1) {
+      // Several windows per launch: the group's chains have stored their appended rows (and pushed them to the peers'
+      // replicas) before the barrier; ONE thread fences at GPU scope -- measured 17 % of the chain phase when every chain's
+      // warp did it on its own last iteration -- and publishes the append: to the local readers (gdone, counters), to the
+      // confirmer CTA (counters) and, in this rank's shared header, to the peers that fetch rows from this archive (my_pub).
+      __threadfence();
+      if (P.ww_gdone) atomicAdd(P.ww_gdone + it.grp, (uint32_t)nch_cta);
+      if (P.my_pub) *reinterpret_cast<volatile uint64_t *>(P.my_pub + it.grp) = P.ww_k0 + (uint64_t)blk + 1u;
+      atomicAdd(counters + blk, (uint32_t)nch_cta);
+    }
     if (P.dbg && tid == 0) {   // profiling aid: cycles of every CTA's batches by phase, summed over the grid
       unsigned long long *acc = reinterpret_cast<unsigned long long *>(P.dbg) + 60;
       const long long tp4 = clock64();
