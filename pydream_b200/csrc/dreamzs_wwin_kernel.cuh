@@ -932,7 +932,11 @@ __global__ void __launch_bounds__(WW_THREADS, DZ_WW_MINBLOCKS) dreamzs_wwin_kern
       // replicas) before the barrier; ONE thread fences at GPU scope -- measured 17 % of the chain phase when every chain's
       // warp did it on its own last iteration -- and publishes the append: to the local readers (gdone, counters), to the
       // confirmer CTA (counters) and, in this rank's shared header, to the peers that fetch rows from this archive (my_pub).
+#ifdef DZ_WW_SC_FENCE
       __threadfence();
+#else
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");   // (a release is all the publication needs; __threadfence() is fence.sc)
+#endif
       if (P.ww_gdone) atomicAdd(P.ww_gdone + it.grp, (uint32_t)nch_cta);
       if (P.my_pub) *reinterpret_cast<volatile uint64_t *>(P.my_pub + it.grp) = P.ww_k0 + (uint64_t)blk + 1u;
       atomicAdd(counters + blk, (uint32_t)nch_cta);
