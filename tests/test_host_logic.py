@@ -282,3 +282,30 @@ def test_whitening_factor_and_packing():
     bad = np.eye(4)
     bad[3, 3] = -1.0
     assert whitening_factor(bad) is None
+
+
+def test_draw_ws_bytes_host_function():
+    """dreamzs_draw_ws_bytes (include/dreamzs.h) is host arithmetic: records of the two-stage steps."""
+    import ctypes as C
+    lib = _cabi.load()
+
+    def cfg(**kw):
+        base = dict(abi_version=_cabi.ABI_VERSION, ndim=10, ld=12, nchains_global=4096, chain_begin=0, nchains_local=4096, nCR=3,
+                    ngamma=1, nDEpairs=1, multitry=5, hardboundaries=1, history_thin=10, target_kind=2, flags=0, snooker=.1,
+                    p_gamma_unity=.2, lamb=.05, zeta=1e-12, seed=1)
+        base.update(kw)
+        return _cabi.Config(**base)
+
+    f = lambda c, n: int(lib.dreamzs_draw_ws_bytes(C.byref(c), n))
+    # multi-try: 8 scalars + (2k-1) points x (A[ld] + B[ld]) doubles per (chain, iteration); C3: 1792 B
+    assert f(cfg(), 10) == 4096 * 10 * (8 + 9 * 2 * 12) * 8
+    assert f(cfg(multitry=8), 3) == 4096 * 3 * (8 + 15 * 2 * 12) * 8
+    assert f(cfg(ndim=40, ld=40, multitry=4), 1) == 0            # a point needs more than 8 lanes
+    assert f(cfg(ndim=20, ld=20, multitry=5), 1) == 0            # five 8-lane points do not fit a warp
+    assert f(cfg(flags=_cabi.FLAG_GENERIC_KERNEL), 10) == 0
+    # single try: 4 + 2 ld doubles per (chain, iteration), whole windows while they fit the budget
+    per = 8192 * (4 + 2 * 200) * 8
+    assert f(cfg(ndim=200, ld=200, nchains_global=8192, nchains_local=8192, multitry=1, target_kind=3), 10) == 10 * per
+    assert f(cfg(ndim=200, ld=200, nchains_global=8192, nchains_local=8192, multitry=1, target_kind=3), 1000) == (1024 * 2 ** 20 // per) * per
+    assert f(cfg(multitry=1, target_kind=5), 10) == 0            # caller-evaluated likelihoods use the split step
+    assert f(cfg(), 0) == 0
