@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, 'libdreamzs.so')
 STEP_VARIANTS = [(4, 1), (8, 1), (16, 1), (32, 1), (32, 2), (32, 4), (32, 8)]
 GAUSS_VARIANTS = [7, 8]
 GWIN_VARIANTS = [7, 8]
-MTP_VARIANTS = [4, 8]
+MTP_VARIANTS = [(2, 1), (2, 2), (4, 1), (4, 2), (8, 1), (8, 2)]
 PLAIN_UNITS = ['dreamzs_cabi.cu', 'dreamzs_adapt.cu', 'dreamzs_gr.cu', 'dreamzs_pt.cu', 'dreamzs_wwin_inst.cu']
 
 # -fmad=false: parity-sensitive element-wise arithmetic must round like numpy;
@@ -68,9 +68,9 @@ def build(force=False, verbose=False):
     for g, r in STEP_VARIANTS:
         jobs.append((os.path.join(CSRC, 'dreamzs_st2_inst.cu'), os.path.join(OBJ, 'st2_%d_%d.o' % (g, r)),
                      ['-DDZ_G=%d' % g, '-DDZ_R=%d' % r], hdr_mtime, force))
-    for g in MTP_VARIANTS:
-        jobs.append((os.path.join(CSRC, 'dreamzs_mtp_inst.cu'), os.path.join(OBJ, 'mtp_%d.o' % g),
-                     ['-DDZ_G=%d' % g], hdr_mtime, force))
+    for g, r in MTP_VARIANTS:
+        jobs.append((os.path.join(CSRC, 'dreamzs_mtp_inst.cu'), os.path.join(OBJ, 'mtp_%d_%d.o' % (g, r)),
+                     ['-DDZ_G=%d' % g, '-DDZ_R=%d' % r], hdr_mtime, force))
     for u in PLAIN_UNITS:
         jobs.append((os.path.join(CSRC, u), os.path.join(OBJ, u.replace('.cu', '.o')), [], hdr_mtime, force))
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:

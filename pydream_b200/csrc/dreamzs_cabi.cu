@@ -11,8 +11,9 @@ using namespace dreamzs;
   int dreamzs_launch_st2_##g##_##r(const dreamzs::StepParams &, int, size_t, cudaStream_t);
 DZ_DECL(4, 1) DZ_DECL(8, 1) DZ_DECL(16, 1) DZ_DECL(32, 1) DZ_DECL(32, 2) DZ_DECL(32, 4) DZ_DECL(32, 8)
 #undef DZ_DECL
-int dreamzs_launch_mtp_4(const dreamzs::StepParams &, size_t, cudaStream_t);
-int dreamzs_launch_mtp_8(const dreamzs::StepParams &, size_t, cudaStream_t);
+#define DZ_DECL_MTP(g, r) int dreamzs_launch_mtp_##g##_##r(const dreamzs::StepParams &, cudaStream_t);
+DZ_DECL_MTP(2, 1) DZ_DECL_MTP(2, 2) DZ_DECL_MTP(4, 1) DZ_DECL_MTP(4, 2) DZ_DECL_MTP(8, 1) DZ_DECL_MTP(8, 2)
+#undef DZ_DECL_MTP
 int dreamzs_launch_gauss_7(const dreamzs::StepParams &, cudaStream_t);
 int dreamzs_launch_gauss_8(const dreamzs::StepParams &, cudaStream_t);
 size_t dreamzs_launch_gauss_smem_bytes(const dreamzs_config &cfg, int TC);
@@ -83,12 +84,12 @@ static bool gwin_eligible(const StepParams &P) {
          !(cfg.flags & DREAMZS_FLAG_NO_WINDOW_KERNEL) && dreamzs_gwin_usable(cfg, 8);
 }
 
-// multi-try with k points side by side in a warp: lane-groups of 4 (ld <= 16) or 8 (ld <= 32) lanes per point
+// multi-try with the k points of a batch side by side: k lane-groups of G lanes per chain, R chunks per lane (mtp_layout)
 static bool mtp_eligible(const StepParams &P) {
   const dreamzs_config &cfg = P.cfg;
-  const int chunks = cfg.ld / 4, G = chunks <= 4 ? 4 : 8;
-  return cfg.multitry > 1 && !P.ext_phase && !P.init_only && chunks <= 8 && cfg.multitry <= 32 / G &&
-         !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL);
+  int G = 0, R = 0;
+  return cfg.multitry > 1 && !P.ext_phase && !P.init_only && !(cfg.flags & DREAMZS_FLAG_GENERIC_KERNEL) &&
+         mtp_layout(cfg.ld, cfg.multitry, G, R);
 }
 
 // two-stage single-try step (dreamzs_st2_kernel.cuh): bytes of one iteration's records, and how many iterations' worth to
@@ -151,14 +152,12 @@ static int dispatch(StepParams &P, cudaStream_t stream) {
   // multi-try iteration with the points of a batch side by side, a warp per chain (dreamzs_mtp_kernel.cuh): two kernels
   // (draws of the window, then the chains) when the caller gave scratch for the draws, else fused
   if (mtp_eligible(P)) {
-    const int PP = 32 / G;
-    const size_t chain_b = (size_t)(threads / 32) * ((size_t)PP * cfg.ld + 3 * DREAMZS_MAX_MULTITRY) * sizeof(double);
-    const size_t table_b = (size_t)((P.table_doubles + 1) & ~1) * sizeof(double);
-    P.table_in_smem = (table_b + chain_b <= 200 * 1024) ? 1 : 0;
-    P.nslots = PP;
-    if (P.st.draw_ws && (P.st.draw_ws_bytes < dreamzs_draw_ws_bytes(&cfg, P.niter))) P.st.draw_ws = nullptr;
-    const size_t smem_b = chain_b + (P.table_in_smem ? table_b : 0);
-    return G == 4 ? dreamzs_launch_mtp_4(P, smem_b, stream) : dreamzs_launch_mtp_8(P, smem_b, stream);
+    int g = 0, r = 0;
+    mtp_layout(cfg.ld, cfg.multitry, g, r);
+    if (P.st.draw_ws && P.st.draw_ws_bytes < dreamzs_draw_ws_bytes(&cfg, P.niter)) P.st.draw_ws = nullptr;
+#define DZ_CASE(a, b) if (g == a && r == b) return dreamzs_launch_mtp_##a##_##b(P, stream);
+    DZ_CASE(2, 1) DZ_CASE(2, 2) DZ_CASE(4, 1) DZ_CASE(4, 2) DZ_CASE(8, 1) DZ_CASE(8, 2)
+#undef DZ_CASE
   }
   // single try with scratch for the draws: draw kernel + chain kernel per sub-span of the window (dreamzs_st2_kernel.cuh)
   if (cfg.multitry == 1 && !P.ext_phase && !P.init_only && P.st.draw_ws && P.st.draw_ws_bytes >= st2_iter_bytes(cfg) &&

@@ -1,7 +1,7 @@
-// Point-parallel multi-try kernel: one translation unit per lane-group width, compiled with -DDZ_G=<lanes per point>.
+// Point-parallel multi-try kernels: one translation unit per layout, compiled with -DDZ_G=<lanes per point> -DDZ_R=<chunk rounds>.
 #include "dreamzs_mtp_kernel.cuh"
-#define DZ_CAT2(a) dreamzs_launch_mtp_##a
-#define DZ_CAT(a) DZ_CAT2(a)
-int DZ_CAT(DZ_G)(const dreamzs::StepParams &P, size_t smem, cudaStream_t stream) {
-  return dreamzs::launch_mtp<DZ_G>(P, smem, stream);
+#define DZ_CAT2(a, b) dreamzs_launch_mtp_##a##_##b
+#define DZ_CAT(a, b) DZ_CAT2(a, b)
+int DZ_CAT(DZ_G, DZ_R)(const dreamzs::StepParams &P, cudaStream_t stream) {
+  return dreamzs::launch_mtp<DZ_G, DZ_R>(P, stream);
 }

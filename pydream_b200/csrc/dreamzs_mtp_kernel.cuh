@@ -1,88 +1,100 @@
-// Point-parallel multi-try kernel (MT-DREAM(ZS), pydream/Dream.py:270-323, 839-917), sm_100a.
+// Point-parallel multi-try kernels (MT-DREAM(ZS), pydream/Dream.py:270-323, 839-917), sm_100a.
 //
-// The generic kernel (dreamzs_step_kernel.cuh) gives a chain ONE lane-group of G lanes and walks the 2k-1 points of a
-// multi-try iteration one after the other: at the C3 shape (d = 10, k = 5, 4096 chains) that is 4 lanes per chain, 3.5
-// warps per SM and nine dependent rounds of draws + archive gathers + log-density per iteration.  Here a chain owns a
-// whole WARP: 32 / G lane-groups, one per point of the batch.  The k proposals are drawn, gathered, bounded and evaluated
-// side by side, then -- around the selected one -- the k-1 reference points: two rounds instead of 2k-1, and 32 / G times
-// the warps in flight.  Every variate is a function of (seed, chain, iteration, stream, call number, block), so the
-// points need no ordering among themselves except for the data-dependent rand() calls of the boundary redraws, whose
-// call numbers are an exclusive prefix over the points (bounds_pp below).
+// The generic kernel (dreamzs_step_kernel.cuh) gives a chain ONE lane-group and walks the 2k-1 points of a multi-try
+// iteration one after the other: at the C3 shape (d = 10, k = 5, 4096 chains) that is 4 lanes per chain, 3.5 warps per SM
+// and nine dependent rounds of draws + archive gathers + log-density per iteration.  Here a chain owns k lane-groups of G
+// lanes, one per point of a batch (a lane holds R chunks of 4 dimensions), and a warp holds as many chains as fit:
+// d = 10, k = 5 -> G = 2, R = 2: ten lanes per chain, three chains per warp.  The k proposals are assembled, bounded and
+// evaluated side by side, then -- around the selected one -- the k-1 reference points: two rounds instead of 2k-1.  Every
+// variate is a function of (seed, chain, iteration, stream, call number, block), so the points need no ordering among
+// themselves except for the data-dependent rand() calls of the boundary redraws, whose call numbers are an exclusive
+// prefix over the points (bounds_pp below).  All synchronisation is per chain (MtLay::cmask): the chains of a warp
+// diverge freely (snooker / DE iterations, regenerated batches).
 //
-// Draws, arithmetic and decisions are those of dreamzs_step_kernel<G, 1, true> / the oracle (the device functions are
+// Draws, arithmetic and decisions are those of dreamzs_step_kernel<G, R, true> / the oracle (the device functions are
 // shared); the chain state is replicated in every lane-group.
 #pragma once
 #include "dreamzs_step_kernel.cuh"
 
 namespace dreamzs {
 
+// where a lane sits: its chain's lanes (mask, first lane), its lane within the chain, its point
+struct MtLay { unsigned cmask; int cbase, cl, pt; };
+
 // Boundary handling of one batch, points side by side (pydream/Dream.py:734-791).  The sequential form (apply_bounds)
 // makes one rand() call per point and per non-empty pass (lower set, then upper set) in point order: point p's calls
 // start after those of the points before it.
-template <int G>
-__device__ __forceinline__ void bounds_redraw(const Ctx<G, 1> &c, const Stream &s, uint32_t call, unsigned m, double (&p)[1][4]) {
+template <int G, int R>
+__device__ __forceinline__ void bounds_redraw(const Ctx<G, R> &c, const Stream &s, uint32_t call, unsigned m, double (&p)[R][4]) {
   const StepParams &P = c.P;
-  const int mine = __popc(m & 15u);
-  int incl = mine;
+  int before_round = 0;  // out-of-bounds dims in earlier rounds (all lanes): ranks run in dimension order = chunk order
 #pragma unroll
-  for (int o = 1; o < G; o <<= 1) {
-    const int t = __shfl_up_sync(c.gmask, incl, o, G);
-    if (c.g >= o) incl += t;
-  }
-  int rank = incl - mine;
+  for (int r = 0; r < R; ++r) {
+    const int mine = __popc((m >> (4 * r)) & 15u);
+    int incl = mine;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if ((m >> j) & 1u) {
-      const int i = c.dim0(0) + j;
-      const uint4 w = s.block(call, ST_RAND, (uint32_t)(rank >> 2));
-      const uint32_t ww = (rank & 3) == 0 ? w.x : (rank & 3) == 1 ? w.y : (rank & 3) == 2 ? w.z : w.w;
-      const double mn = P.st.mins[i], mx = P.st.maxs[i];
-      p[0][j] = mn + u32_of(ww) * (mx - mn);
-      ++rank;
+    for (int o = 1; o < G; o <<= 1) {
+      const int t = __shfl_up_sync(c.gmask, incl, o, G);
+      if (c.g >= o) incl += t;
     }
+    int rank = before_round + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((m >> (4 * r + j)) & 1u) {
+        const int i = c.dim0(r) + j;
+        const uint4 w = s.block(call, ST_RAND, (uint32_t)(rank >> 2));
+        const uint32_t ww = (rank & 3) == 0 ? w.x : (rank & 3) == 1 ? w.y : (rank & 3) == 2 ? w.z : w.w;
+        const double mn = P.st.mins[i], mx = P.st.maxs[i];
+        p[r][j] = mn + u32_of(ww) * (mx - mn);
+        ++rank;
+      }
+    before_round += gsum_int<G>(mine, c.gmask);
+  }
 }
-template <int G>
-__device__ __forceinline__ void bounds_pp(const Ctx<G, 1> &c, Stream &s, bool act, int n, int pt, double (&p)[1][4]) {
+template <int G, int R>
+__device__ __forceinline__ void bounds_pp(const Ctx<G, R> &c, const MtLay &L, Stream &s, bool act, int n, double (&p)[R][4]) {
   const StepParams &P = c.P;
   unsigned lo = 0, hi = 0;
   int tl = 0, th = 0;
   if (act) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = c.dim0(0) + j;
-      if (i < c.d) {
-        const double mn = P.st.mins[i], mx = P.st.maxs[i];
-        double v = p[0][j];
-        if (v < mn) v = 2 * mn - v;
-        else if (v > mx) v = 2 * mx - v;
-        p[0][j] = v;
-        if (v < mn) lo |= 1u << j;
-        if (v > mx) hi |= 1u << j;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = c.dim0(r) + j;
+        if (i < c.d) {
+          const double mn = P.st.mins[i], mx = P.st.maxs[i];
+          double v = p[r][j];
+          if (v < mn) v = 2 * mn - v;
+          else if (v > mx) v = 2 * mx - v;
+          p[r][j] = v;
+          if (v < mn) lo |= 1u << (4 * r + j);
+          if (v > mx) hi |= 1u << (4 * r + j);
+        }
       }
-    }
     tl = gsum_int<G>(__popc(lo), c.gmask);
     th = gsum_int<G>(__popc(hi), c.gmask);
   }
   const int cnt = (tl > 0) + (th > 0);
   int base = 0, total = 0;
   for (int q = 0; q < n; ++q) {
-    const int cq = __shfl_sync(0xffffffffu, cnt, q * G);
-    if (q < pt) base += cq;
+    const int cq = __shfl_sync(L.cmask, cnt, L.cbase + q * G);
+    if (q < L.pt) base += cq;
     total += cq;
   }
   if (total == 0) return;
   if (act) {
-    if (tl > 0) bounds_redraw<G>(c, s, s.n_rand + (uint32_t)base, lo, p);
-    if (th > 0) bounds_redraw<G>(c, s, s.n_rand + (uint32_t)base + (tl > 0 ? 1u : 0u), hi, p);
+    if (tl > 0) bounds_redraw<G, R>(c, s, s.n_rand + (uint32_t)base, lo, p);
+    if (th > 0) bounds_redraw<G, R>(c, s, s.n_rand + (uint32_t)base + (tl > 0 ? 1u : 0u), hi, p);
   }
   s.n_rand += (uint32_t)total;
 }
 
 // One batch of n points around `ctr` (generate_proposal_points, Dream.py:628-732): lane-group pt makes point pt, leaves it
 // in `out` / its slot and its scalars in pri / lik / snk [pt].  Returns np.any(gamma == 1.0) of the batch.
-template <int G>
-__device__ __noinline__ bool mtp_batch(const Ctx<G, 1> &c, Stream &s, const Decisions &dc, int n, int pt, int64_t M,
-                                       const double (&ctr)[1][4], double *slot, double (&out)[1][4], double *pri,
+template <int G, int R>
+__device__ __noinline__ bool mtp_batch(const Ctx<G, R> &c, const MtLay L, Stream &s, const Decisions &dc, int n, int64_t M,
+                                       const double (&ctr)[R][4], double *slot, double (&out)[R][4], double *pri,
                                        double *lik, double *snk) {
   const StepParams &P = c.P;
   const Bases b = {s.n_sample, s.n_normal, s.n_uvec};
@@ -94,30 +106,32 @@ __device__ __noinline__ bool mtp_batch(const Ctx<G, 1> &c, Stream &s, const Deci
     gamma = 1.2 + (2.2 - 1.2) * uniform_scalar(s);
     if (gamma == 1.0) gamma_one = true;
   }
+  const int pt = L.pt;
   const bool act = pt < n;
   double sl = 0.0;
-  out[0][0] = out[0][1] = out[0][2] = out[0][3] = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r][0] = out[r][1] = out[r][2] = out[r][3] = 0.0;
   if (act) {
     if (dc.run_snooker) {
       double D;
-      snooker_point<G, 1>(c, s, b, n, pt, M, gamma, ctr, out, sl, D);
+      snooker_point<G, R>(c, s, b, n, pt, M, gamma, ctr, out, sl, D);
     } else {
       s.n_multinomial = m_base + pt;                         // gamma-unity draw of point pt
-      de_point<G, 1>(c, s, dc, b, n, pt, M, ctr, out, gamma_one);
+      de_point<G, R>(c, s, dc, b, n, pt, M, ctr, out, gamma_one);
     }
   }
-  if (P.cfg.hardboundaries && !P.all_flat) bounds_pp<G>(c, s, act, n, pt, out);
+  if (P.cfg.hardboundaries && !P.all_flat) bounds_pp<G, R>(c, L, s, act, n, out);
   if (act) {
-    store_slot<G, 1>(c, slot, out);
+    store_slot<G, R>(c, slot, out);
     __syncwarp(c.gmask);
     double pr, lk;
-    eval_logp<G, 1>(c, out, slot, pr, lk);
+    eval_logp<G, R>(c, out, slot, pr, lk);
     if (c.g == 0) { pri[pt] = pr; lik[pt] = lk; snk[pt] = sl; }
   }
-  gamma_one = __any_sync(0xffffffffu, gamma_one);
+  gamma_one = __any_sync(L.cmask, gamma_one);
   if (dc.run_snooker) s.n_sample = b.s + 3 * n;
   else { s.n_sample = b.s + n; s.n_normal = b.n + n; s.n_uvec = b.u + 2 * n; s.n_multinomial = m_base + n; }
-  __syncwarp();
+  __syncwarp(L.cmask);
   return gamma_one;
 }
 
@@ -125,36 +139,39 @@ __device__ __noinline__ bool mtp_batch(const Ctx<G, 1> &c, Stream &s, const Deci
 struct MtOutcome { int sel; bool gamma_one, accepted; double new_prior, new_like; };
 
 // The multi-try selection and acceptance arithmetic is a handful of exp / log / divide on k (or 2k) numbers.  Every lane
-// of the warp would compute all of them -- and on B200 a warp-wide fp64 instruction costs the same two issue cycles of
-// the one fp64 pipe whether one lane needs it or 32 -- so lane l computes the l-th exponential only and the values are
-// exchanged by shuffles; the sums run in the reference's order on every lane (same bits everywhere).
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// of the chain would compute all of them -- and on B200 a warp-wide fp64 instruction costs the same two issue cycles of
+// the one fp64 pipe whether one lane needs it or 32 -- so lane l of the chain computes the l-th exponential only and the
+// values are exchanged by shuffles; the sums run in the reference's order on every lane (same bits everywhere).
+// (A chain has k G >= 2k lanes for G >= 2; with G = 1 the lanes past the chain's compute nothing and the second half of
+// the exponentials of the ratio takes a second pass.)
+__device__ __forceinline__ double shfl_d(unsigned mask, double v, int src) { return __shfl_sync(mask, v, src); }
 
 // mt_choose_proposal_pt (Dream.py:883-917) given the uniform of the multinomial draw: inverse CDF on a running sum
-__device__ __forceinline__ int mt_choose(const double *pri, const double *lik, double Tc, int k, double u, int lane) {
+__device__ __forceinline__ int mt_choose(const MtLay &L, const double *pri, const double *lik, double Tc, int k, double u) {
   double mx = Tc * lik[0] + pri[0];
   for (int p = 1; p < k; ++p) { const double v = Tc * lik[p] + pri[p]; if (v > mx) mx = v; }
-  const int lp = lane < k ? lane : 0;
-  const double e = exp((Tc * lik[lp] + pri[lp]) - mx);        // lane p: exp(log_ps[p] - max)
+  const int lp = L.cl < k ? L.cl : 0;
+  const double e = exp((Tc * lik[lp] + pri[lp]) - mx);        // lane p of the chain: exp(log_ps[p] - max)
   double sum = 0.0;
-  for (int p = 0; p < k; ++p) { const double ep = shfl_d(e, p); sum = (p == 0) ? ep : sum + ep; }
+  for (int p = 0; p < k; ++p) { const double ep = shfl_d(L.cmask, e, L.cbase + p); sum = (p == 0) ? ep : sum + ep; }
   const double pr = e / sum;                                   // lane p: the probability of point p
   double acc = 0.0;
   int idx = k - 1;
   bool found = false;
   for (int p = 0; p < k; ++p) {
-    acc = acc + shfl_d(pr, p);
+    acc = acc + shfl_d(L.cmask, pr, L.cbase + p);
     if (!found && u < acc) { idx = p; found = true; }
   }
   return idx;
 }
 
-// log of the multi-try acceptance ratio, Dream.py:304-323 (reference point k-1 is the current state); k <= 16 lanes
-__device__ __forceinline__ double mt_ratio(const double *pri, const double *lik, const double *snk, const double *rpri,
+// log of the multi-try acceptance ratio, Dream.py:304-323 (reference point k-1 is the current state); the chain has at
+// least 2k lanes (G >= 2)
+__device__ __forceinline__ double mt_ratio(const MtLay &L, const double *pri, const double *lik, const double *snk, const double *rpri,
                                            const double *rlik, const double *rsnk, double last_prior, double last_like,
-                                           double Tc, int k, bool run_snooker, int lane) {
-  // lane p < k holds the proposal term of point p, lane k + p its reference term
-  const int p = lane < k ? lane : (lane < 2 * k ? lane - k : 0);
+                                           double Tc, int k, bool run_snooker) {
+  // lane p < k of the chain holds the proposal term of point p, lane k + p its reference term
+  const int p = L.cl < k ? L.cl : (L.cl < 2 * k ? L.cl - k : 0);
   const double lps = Tc * lik[p] + pri[p];
   const double rl = (p == k - 1) ? last_like : rlik[p], rp = (p == k - 1) ? last_prior : rpri[p];
   const double rlps = Tc * rl + rp;
@@ -163,16 +180,16 @@ __device__ __forceinline__ double mt_ratio(const double *pri, const double *lik,
     const double rs = (p == k - 1) ? 0.0 : rsnk[p];
     tpv = lps + snk[p]; trv = rlps + rs + snk[p];
   } else { tpv = lps; trv = rlps; }
-  double m2 = shfl_d(tpv, 0);
+  double m2 = shfl_d(L.cmask, tpv, L.cbase);
   for (int q = 0; q < k; ++q) {
-    const double a = shfl_d(tpv, q), b = shfl_d(trv, q);
+    const double a = shfl_d(L.cmask, tpv, L.cbase + q), b = shfl_d(L.cmask, trv, L.cbase + q);
     if (a > m2) m2 = a;
     if (b > m2) m2 = b;
   }
-  const double ex = exp((lane < k ? tpv : trv) - m2);
+  const double ex = exp((L.cl < k ? tpv : trv) - m2);
   double swp = 0.0, swr = 0.0;
   for (int q = 0; q < k; ++q) {
-    const double a = shfl_d(ex, q), b = shfl_d(ex, k + q);
+    const double a = shfl_d(L.cmask, ex, L.cbase + q), b = shfl_d(L.cmask, ex, L.cbase + k + q);
     swp = q == 0 ? a : swp + a; swr = q == 0 ? b : swr + b;
   }
   return nan_to_num(log(swp / swr));                                                 // Dream.py:320-323
@@ -182,10 +199,10 @@ __device__ __forceinline__ double mt_ratio(const double *pri, const double *lik,
 // (regenerated while none has a finite log-posterior), the choice, the reference set, the acceptance test.  q = the
 // selected proposal.  Out of line: the fused kernel's loop body, and the two-stage kernel's way out when a batch has to be
 // regenerated (the draws made ahead by the draw kernel no longer apply then).
-template <int G>
-__device__ __noinline__ void mtp_iteration(const Ctx<G, 1> &c, int64_t iter, uint32_t c_global, int pt, double *slot,
-                                           const double (&x0)[1][4], double last_prior, double last_like, double Tc,
-                                           int64_t M, Decisions &dc, double (&q)[1][4], MtOutcome &o) {
+template <int G, int R>
+__device__ __noinline__ void mtp_iteration(const Ctx<G, R> &c, const MtLay L, int64_t iter, uint32_t c_global, double *slot,
+                                           const double (&x0)[R][4], double last_prior, double last_like, double Tc,
+                                           int64_t M, Decisions &dc, double (&q)[R][4], MtOutcome &o) {
   const StepParams &P = c.P;
   const int k = P.cfg.multitry, ld = c.ld;
   double *pri = c.scal, *lik = c.scal + DREAMZS_MAX_MULTITRY, *snk = c.scal + 2 * DREAMZS_MAX_MULTITRY;
@@ -201,43 +218,45 @@ __device__ __noinline__ void mtp_iteration(const Ctx<G, 1> &c, int64_t iter, uin
     dc.delta = 1 + (int)(((uint64_t)w.x * (uint64_t)P.cfg.nDEpairs) >> 32);
   }
   dc.lvl_idx = multinomial_index(s, P.st.gamma_probs, P.cfg.ngamma);                 // set_gamma_level, :585-599
-  double pp[1][4];
+  double pp[R][4];
   for (int guard = 0;; ++guard) {                                                    // Dream.py:278-289
-    o.gamma_one = mtp_batch<G>(c, s, dc, k, pt, M, x0, slot, pp, pri, lik, snk);
+    o.gamma_one = mtp_batch<G, R>(c, L, s, dc, k, M, x0, slot, pp, pri, lik, snk);
     bool anyfinite = false;
     for (int p = 0; p < k; ++p) anyfinite |= isfinite(Tc * lik[p] + pri[p]);
     if (anyfinite || guard >= 1000) break;
   }
   {
     const uint4 w = s.block(s.n_multinomial++, ST_MULTINOMIAL, 0);
-    o.sel = mt_choose(pri, lik, Tc, k, u53_of(w.x, w.y), (int)(threadIdx.x & 31));
+    o.sel = mt_choose(L, pri, lik, Tc, k, u53_of(w.x, w.y));
   }
-  load_slot<G, 1>(c, c.slots + (size_t)o.sel * ld, q);
+  load_slot<G, R>(c, c.slots + (size_t)o.sel * ld, q);
   o.new_prior = pri[o.sel]; o.new_like = lik[o.sel];
-  __syncwarp();   // every lane-group has read the selected point before the reference set overwrites the slots
-  o.gamma_one = mtp_batch<G>(c, s, dc, k - 1, pt, M, q, slot, pp, rpri, rlik, rsnk);   // reference set, Dream.py:295-303
-  const double mr = mt_ratio(pri, lik, snk, rpri, rlik, rsnk, last_prior, last_like, Tc, k, dc.run_snooker != 0, (int)(threadIdx.x & 31));
+  __syncwarp(L.cmask);   // every lane-group has read the selected point before the reference set overwrites the slots
+  o.gamma_one = mtp_batch<G, R>(c, L, s, dc, k - 1, M, q, slot, pp, rpri, rlik, rsnk);   // reference set, Dream.py:295-303
+  const double mr = mt_ratio(L, pri, lik, snk, rpri, rlik, rsnk, last_prior, last_like, Tc, k, dc.run_snooker != 0);
   o.accepted = false;
   if (isfinite(mr)) o.accepted = log(uniform_scalar(s)) < mr;                        // metrop_select, :980-998
 }
 
 // State update (Dream.py:336-347: "accepted" is inferred from the state having changed), trace row (core.py:114-115)
-// and archive append (record_history, Dream.py:360-362, 919-938) of one iteration; lane-group 0 writes.
-template <int G>
-__device__ __forceinline__ void mt_commit(const Ctx<G, 1> &c, const StepParams &P, int it, int64_t iter, int c_local,
-                                          uint32_t c_global, bool writer, int64_t M, const Decisions &dc, const MtOutcome &o,
-                                          const double (&q)[1][4], double (&x0)[1][4], double &last_prior, double &last_like,
+// and archive append (record_history, Dream.py:360-362, 919-938) of one iteration; lane-group 0 of the chain writes.
+template <int G, int R>
+__device__ __forceinline__ void mt_commit(const Ctx<G, R> &c, const MtLay &L, const StepParams &P, int it, int64_t iter, int c_local,
+                                          uint32_t c_global, int64_t M, const Decisions &dc, const MtOutcome &o,
+                                          const double (&q)[R][4], double (&x0)[R][4], double &last_prior, double &last_like,
                                           double Tc) {
   int changed = 0;
   if (o.accepted) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { changed |= (q[0][j] != x0[0][j]); x0[0][j] = q[0][j]; }
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { changed |= (q[r][j] != x0[r][j]); x0[r][j] = q[r][j]; }
   }
   changed = gsum_int<G>(changed, c.gmask) != 0;
   if (changed) { last_prior = o.new_prior; last_like = o.new_like; }
   const int64_t trow = P.tr.trace_offset + it;
-  if (writer) {
-    store_row<G, 1>(c, P.tr.trace + ((size_t)c_local * P.tr.trace_iters + trow) * c.ld, x0);
+  if (L.pt == 0) {
+    store_row<G, R>(c, P.tr.trace + ((size_t)c_local * P.tr.trace_iters + trow) * c.ld, x0);
     if (c.g == 0) {
       P.tr.trace_logp[(size_t)c_local * P.tr.trace_iters + trow] = Tc * last_like + last_prior;   // core.py:115 (T = 1), :176
       if (P.tr.decisions)
@@ -245,8 +264,8 @@ __device__ __forceinline__ void mt_commit(const Ctx<G, 1> &c, const StepParams &
             pack_decision(changed, dc.run_snooker, dc.cr_idx, dc.lvl_idx, dc.delta, o.sel, o.gamma_one, o.accepted);
     }
     if (iter % P.cfg.history_thin == 0) {   // only the last iteration of a launch may append
-      store_row<G, 1>(c, P.st.Z + (size_t)(M + c_global) * c.ld, x0);
-      for (int pz = 0; pz < P.npeers; ++pz) store_row<G, 1>(c, P.peer_Z[pz] + (size_t)(M + c_global) * c.ld, x0);   // replicas over NVLink
+      store_row<G, R>(c, P.st.Z + (size_t)(M + c_global) * c.ld, x0);
+      for (int pz = 0; pz < P.npeers; ++pz) store_row<G, R>(c, P.peer_Z[pz] + (size_t)(M + c_global) * c.ld, x0);   // replicas over NVLink
       if (P.publish_k) {
         __threadfence_system();
         __syncwarp(c.gmask);
@@ -254,18 +273,18 @@ __device__ __forceinline__ void mt_commit(const Ctx<G, 1> &c, const StepParams &
       }
     }
   }
-  __syncwarp();
+  __syncwarp(L.cmask);
 }
 
 #ifndef DZ_MTP_MINBLOCKS
-#define DZ_MTP_MINBLOCKS 4
+#define DZ_MTP_MINBLOCKS 3
 #endif
 
-// what the multi-try kernels share at entry: the target table staged in shared memory, the chain's context and state
+// what the multi-try kernels share at entry: the target table staged in shared memory, the lane's place, the chain's
+// context and state
 #define DZ_MT_PROLOGUE()                                                                                              \
   extern __shared__ __align__(16) double smem[];                                                                     \
-  constexpr int PP = 32 / G;                      /* points side by side */                                          \
-  const int d = P.cfg.ndim, ld = P.cfg.ld;                                                                           \
+  const int d = P.cfg.ndim, ld = P.cfg.ld, k = P.cfg.multitry;                                                        \
   const double *table = P.st.target_table;                                                                           \
   double *sm_chain = smem;                                                                                           \
   if (P.table_in_smem) {                                                                                             \
@@ -275,25 +294,22 @@ __device__ __forceinline__ void mt_commit(const Ctx<G, 1> &c, const StepParams &
     __syncthreads();                                                                                                 \
   }                                                                                                                  \
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                                                        \
-  const int c_local = blockIdx.x * (blockDim.x >> 5) + warp;                                                         \
-  if (c_local >= P.cfg.nchains_local) return;                                                                        \
-  const int pt = lane / G;                                                                                           \
-  const int per_chain = PP * ld + 3 * DREAMZS_MAX_MULTITRY;                                                          \
-  Ctx<G, 1> c{P, table, sm_chain + (size_t)warp * per_chain, nullptr,                                                \
-              G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1))), lane & (G - 1), d, ld};               \
-  c.scal = c.slots + (size_t)PP * ld;                                                                                \
-  double *slot = c.slots + (size_t)pt * ld;                                                                          \
+  const int LC = k * G, CPW = 32 / LC;                 /* lanes per chain, chains per warp */                        \
+  const int cw = lane / LC;                                                                                          \
+  const int chain_in_cta = warp * CPW + cw;                                                                          \
+  const int c_local = (blockIdx.x * (blockDim.x >> 5) + warp) * CPW + cw;                                            \
+  if (cw >= CPW || c_local >= P.cfg.nchains_local) return;      /* whole chains leave together */                    \
+  MtLay L;                                                                                                           \
+  L.cbase = cw * LC; L.cl = lane - L.cbase; L.pt = L.cl / G;                                                          \
+  L.cmask = (LC == 32 ? 0xffffffffu : ((1u << LC) - 1u)) << L.cbase;                                                  \
+  const int per_chain = k * ld + 3 * DREAMZS_MAX_MULTITRY;                                                           \
+  Ctx<G, R> c{P, table, sm_chain + (size_t)chain_in_cta * per_chain, nullptr,                                        \
+              ((1u << G) - 1u) << (L.cbase + L.pt * G), L.cl - L.pt * G, d, ld};                                      \
+  c.scal = c.slots + (size_t)k * ld;                                                                                 \
+  double *slot = c.slots + (size_t)L.pt * ld;                                                                        \
   const uint32_t c_global = (uint32_t)(P.cfg.chain_begin + c_local);                                                 \
-  const bool writer = pt == 0;                    /* the lane-group that writes the chain's rows */                  \
-  double x0[1][4];                                                                                                   \
-  {                                                                                                                  \
-    const double *xrow = P.st.X + (size_t)c_local * ld;                                                              \
-    const int i0 = c.dim0(0);                                                                                        \
-    if (i0 < ld) {                                                                                                   \
-      const double2 a = *reinterpret_cast<const double2 *>(xrow + i0), b = *reinterpret_cast<const double2 *>(xrow + i0 + 2); \
-      x0[0][0] = a.x; x0[0][1] = a.y; x0[0][2] = b.x; x0[0][3] = b.y;                                                \
-    } else x0[0][0] = x0[0][1] = x0[0][2] = x0[0][3] = 0.0;                                                          \
-  }                                                                                                                  \
+  double x0[R][4];                                                                                                   \
+  load_slot<G, R>(c, P.st.X + (size_t)c_local * ld, x0);                                                             \
   double last_prior = P.st.last_prior[c_local], last_like = P.st.last_like[c_local];                                 \
   const double Tc = P.temperature ? P.temperature[c_local] : 1.0;                                                    \
   const int64_t M = P.archive_rows
@@ -301,26 +317,26 @@ __device__ __forceinline__ void mt_commit(const Ctx<G, 1> &c, const StepParams &
 // Fused form: draws and evaluation in one kernel (used when no draw scratch is given).
 // (__grid_constant__: the out-of-line functions take the parameter block by reference; without it the kernel would copy
 // all of it to local memory first)
-template <int G>
+template <int G, int R>
 __global__ void __launch_bounds__(128, DZ_MTP_MINBLOCKS) dreamzs_mtp_kernel(const __grid_constant__ StepParams P) {
   DZ_MT_PROLOGUE();
   if (P.peer_error && *reinterpret_cast<volatile int32_t *>(P.peer_error) != 0) return;   // an earlier wait timed out: the host raises
   if (P.wait_k) {   // sharded archive: the peers' rows of the previous append must have landed in this replica
     int ok = 1;
-    if (lane == 0) ok = peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error) ? 1 : 0;
-    if (!__shfl_sync(0xffffffffu, ok, 0)) return;   // timed out: states stay as they are
+    if (L.cl == 0) ok = peer_wait(P.my_flags, P.world, P.my_rank, P.wait_k, P.peer_error) ? 1 : 0;
+    if (!__shfl_sync(L.cmask, ok, L.cbase)) return;   // timed out: states stay as they are
   }
 #pragma unroll 1
   for (int it = 0; it < P.niter; ++it) {
     const int64_t iter = P.iter_begin + it;
     Decisions dc;
     MtOutcome o;
-    double q[1][4];
-    mtp_iteration<G>(c, iter, c_global, pt, slot, x0, last_prior, last_like, Tc, M, dc, q, o);
-    mt_commit<G>(c, P, it, iter, c_local, c_global, writer, M, dc, o, q, x0, last_prior, last_like, Tc);
+    double q[R][4];
+    mtp_iteration<G, R>(c, L, iter, c_global, slot, x0, last_prior, last_like, Tc, M, dc, q, o);
+    mt_commit<G, R>(c, L, P, it, iter, c_local, c_global, M, dc, o, q, x0, last_prior, last_like, Tc);
   }
-  if (writer) {
-    store_row<G, 1>(c, P.st.X + (size_t)c_local * ld, x0);
+  if (L.pt == 0) {
+    store_row<G, R>(c, P.st.X + (size_t)c_local * ld, x0);
     if (c.g == 0) { P.st.last_prior[c_local] = last_prior; P.st.last_like[c_local] = last_like; }
   }
 }
@@ -450,65 +466,74 @@ __global__ void __launch_bounds__(256, 4) dreamzs_mtdraw_kernel(const __grid_con
 }
 
 // one batch of the chain kernel: lane-group pt assembles point pt from the record, bounds, log-density
-template <int G>
-__device__ __forceinline__ void mt2_batch(const Ctx<G, 1> &c, Stream &s, bool run_snooker, double gamma, int n, int pt,
-                                          const double (&ctr)[1][4], const double (&A)[1][4], double (&B)[1][4], double *slot,
+template <int G, int R>
+__device__ __forceinline__ void mt2_batch(const Ctx<G, R> &c, const MtLay &L, Stream &s, bool run_snooker, double gamma, int n,
+                                          const double (&ctr)[R][4], const double (&A)[R][4], double (&B)[R][4], double *slot,
                                           double *pri, double *lik, double *snk) {
   const StepParams &P = c.P;
-  const bool act = pt < n;
-  double out[1][4] = {{0.0, 0.0, 0.0, 0.0}};
+  const bool act = L.pt < n;
+  double out[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r][0] = out[r][1] = out[r][2] = out[r][3] = 0.0;
   double sl = 0.0;
   if (act) {
     if (run_snooker) {
       double D;
-      snooker_compute<G, 1>(c, n, gamma, ctr, A, B, out, sl, D);
+      snooker_compute<G, R>(c, n, gamma, ctr, A, B, out, sl, D);
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out[0][j] = ctr[0][j] + A[0][j] + B[0][j];   // Dream.py:717 (centre kept where J = zeta = 0)
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[r][j] = ctr[r][j] + A[r][j] + B[r][j];   // Dream.py:717 (centre kept where J = zeta = 0)
     }
   }
-  if (P.cfg.hardboundaries && !P.all_flat) bounds_pp<G>(c, s, act, n, pt, out);
+  if (P.cfg.hardboundaries && !P.all_flat) bounds_pp<G, R>(c, L, s, act, n, out);
   if (act) {
-    store_slot<G, 1>(c, slot, out);
+    store_slot<G, R>(c, slot, out);
     __syncwarp(c.gmask);
     double pr, lk;
-    eval_logp<G, 1>(c, out, slot, pr, lk);
-    if (c.g == 0) { pri[pt] = pr; lik[pt] = lk; snk[pt] = sl; }
+    eval_logp<G, R>(c, out, slot, pr, lk);
+    if (c.g == 0) { pri[L.pt] = pr; lik[L.pt] = lk; snk[L.pt] = sl; }
   }
-  __syncwarp();
+  __syncwarp(L.cmask);
 }
 
-template <int G>
+template <int G, int R>
 __global__ void __launch_bounds__(128, DZ_MTP_MINBLOCKS) dreamzs_mtchain_kernel(const __grid_constant__ StepParams P) {
   DZ_MT_PROLOGUE();
   if (P.peer_error && *reinterpret_cast<volatile int32_t *>(P.peer_error) != 0) return;   // the draw kernel's wait for the peers timed out
-  const int k = P.cfg.multitry;
   double *pri = c.scal, *lik = c.scal + DREAMZS_MAX_MULTITRY, *snk = c.scal + 2 * DREAMZS_MAX_MULTITRY;
   double *rpri = pri + k, *rlik = lik + k, *rsnk = snk + k;
   const int S = mt2_record_doubles(k, ld);
-  const int i0 = c.dim0(0);
+  const int pt = L.pt;
   const double *rec = P.st.draw_ws + (size_t)c_local * P.niter * S;
 #pragma unroll 1
   for (int it = 0; it < P.niter; ++it, rec += S) {
     const int64_t iter = P.iter_begin + it;
     // the record: scalars, this lane-group's proposal and reference point (neither depends on the chain state)
     if (it + 1 < P.niter)   // the next record: on its way to L1 while this iteration runs
-      for (int o = lane * 16; o < S; o += 32 * 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + S + o));
+      for (int o = L.cl * 16; o < S; o += LC * 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + S + o));
     const double u_sel = rec[0], logu = rec[1], g1 = rec[2], g2 = rec[3];
     const uint2 wd = *reinterpret_cast<const uint2 *>(rec + 4);
-    double A1[1][4] = {{0, 0, 0, 0}}, B1[1][4] = {{0, 0, 0, 0}}, A2[1][4] = {{0, 0, 0, 0}}, B2[1][4] = {{0, 0, 0, 0}};
-    if (i0 < ld) {
-      if (pt < k) {
-        const double *r1 = rec + 8 + (size_t)pt * 2 * ld + i0;
-        const double2 a = *reinterpret_cast<const double2 *>(r1), b = *reinterpret_cast<const double2 *>(r1 + 2);
-        const double2 e = *reinterpret_cast<const double2 *>(r1 + ld), f = *reinterpret_cast<const double2 *>(r1 + ld + 2);
-        A1[0][0] = a.x; A1[0][1] = a.y; A1[0][2] = b.x; A1[0][3] = b.y; B1[0][0] = e.x; B1[0][1] = e.y; B1[0][2] = f.x; B1[0][3] = f.y;
-      }
-      if (pt < k - 1) {
-        const double *r2 = rec + 8 + (size_t)(k + pt) * 2 * ld + i0;
-        const double2 a = *reinterpret_cast<const double2 *>(r2), b = *reinterpret_cast<const double2 *>(r2 + 2);
-        const double2 e = *reinterpret_cast<const double2 *>(r2 + ld), f = *reinterpret_cast<const double2 *>(r2 + ld + 2);
-        A2[0][0] = a.x; A2[0][1] = a.y; A2[0][2] = b.x; A2[0][3] = b.y; B2[0][0] = e.x; B2[0][1] = e.y; B2[0][2] = f.x; B2[0][3] = f.y;
+    double A1[R][4], B1[R][4], A2[R][4], B2[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i0 = c.dim0(r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { A1[r][j] = 0.0; B1[r][j] = 0.0; A2[r][j] = 0.0; B2[r][j] = 0.0; }
+      if (i0 < ld) {
+        if (pt < k) {
+          const double *r1 = rec + 8 + (size_t)pt * 2 * ld + i0;
+          const double2 a = *reinterpret_cast<const double2 *>(r1), b = *reinterpret_cast<const double2 *>(r1 + 2);
+          const double2 e = *reinterpret_cast<const double2 *>(r1 + ld), f = *reinterpret_cast<const double2 *>(r1 + ld + 2);
+          A1[r][0] = a.x; A1[r][1] = a.y; A1[r][2] = b.x; A1[r][3] = b.y; B1[r][0] = e.x; B1[r][1] = e.y; B1[r][2] = f.x; B1[r][3] = f.y;
+        }
+        if (pt < k - 1) {
+          const double *r2 = rec + 8 + (size_t)(k + pt) * 2 * ld + i0;
+          const double2 a = *reinterpret_cast<const double2 *>(r2), b = *reinterpret_cast<const double2 *>(r2 + 2);
+          const double2 e = *reinterpret_cast<const double2 *>(r2 + ld), f = *reinterpret_cast<const double2 *>(r2 + ld + 2);
+          A2[r][0] = a.x; A2[r][1] = a.y; A2[r][2] = b.x; A2[r][3] = b.y; B2[r][0] = e.x; B2[r][1] = e.y; B2[r][2] = f.x; B2[r][3] = f.y;
+        }
       }
     }
     Decisions dc;
@@ -517,59 +542,73 @@ __global__ void __launch_bounds__(128, DZ_MTP_MINBLOCKS) dreamzs_mtchain_kernel(
     dc.CR = (double)(dc.cr_idx + 1) / (double)P.cfg.nCR;
     Stream s; s.init(P.cfg.seed, c_global, (uint32_t)iter);      // (only the boundary redraws draw here)
     MtOutcome o;
-    double q[1][4] = {{x0[0][0], x0[0][1], x0[0][2], x0[0][3]}};
+    double q[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[r][j] = x0[r][j];
     bool fast = true;
 #pragma unroll 1
     for (int bt = 0; bt < 2; ++bt) {   // the proposals around x0, then the reference set around the selected one (one copy of the code)
       if (bt) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { A1[0][j] = A2[0][j]; B1[0][j] = B2[0][j]; }
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { A1[r][j] = A2[r][j]; B1[r][j] = B2[r][j]; }
       }
-      mt2_batch<G>(c, s, dc.run_snooker != 0, bt ? g2 : g1, bt ? k - 1 : k, pt, q, A1, B1, slot, bt ? rpri : pri, bt ? rlik : lik,
-                   bt ? rsnk : snk);
+      mt2_batch<G, R>(c, L, s, dc.run_snooker != 0, bt ? g2 : g1, bt ? k - 1 : k, q, A1, B1, slot, bt ? rpri : pri, bt ? rlik : lik,
+                      bt ? rsnk : snk);
       if (bt == 0) {
         bool anyfinite = false;
         for (int p = 0; p < k; ++p) anyfinite |= isfinite(Tc * lik[p] + pri[p]);
         if (!anyfinite) { fast = false; break; }
-        o.sel = mt_choose(pri, lik, Tc, k, u_sel, lane);
-        load_slot<G, 1>(c, c.slots + (size_t)o.sel * ld, q);
+        o.sel = mt_choose(L, pri, lik, Tc, k, u_sel);
+        load_slot<G, R>(c, c.slots + (size_t)o.sel * ld, q);
         o.new_prior = pri[o.sel]; o.new_like = lik[o.sel];
-        __syncwarp();   // every lane-group has read the selected point before the reference set overwrites the slots
+        __syncwarp(L.cmask);   // every lane-group has read the selected point before the reference set overwrites the slots
       }
     }
     if (fast) {
       o.gamma_one = dc.run_snooker ? g2 == 1.0 : ((wd.y >> k) & ((1u << (k - 1)) - 1u)) != 0u;
-      const double mr = mt_ratio(pri, lik, snk, rpri, rlik, rsnk, last_prior, last_like, Tc, k, dc.run_snooker != 0, lane);
+      const double mr = mt_ratio(L, pri, lik, snk, rpri, rlik, rsnk, last_prior, last_like, Tc, k, dc.run_snooker != 0);
       o.accepted = isfinite(mr) && logu < mr;                                        // metrop_select, Dream.py:980-998
     } else {
-      __syncwarp();
-      mtp_iteration<G>(c, iter, c_global, pt, slot, x0, last_prior, last_like, Tc, M, dc, q, o);
+      __syncwarp(L.cmask);
+      mtp_iteration<G, R>(c, L, iter, c_global, slot, x0, last_prior, last_like, Tc, M, dc, q, o);
     }
-    mt_commit<G>(c, P, it, iter, c_local, c_global, writer, M, dc, o, q, x0, last_prior, last_like, Tc);
+    mt_commit<G, R>(c, L, P, it, iter, c_local, c_global, M, dc, o, q, x0, last_prior, last_like, Tc);
   }
-  if (writer) {
-    store_row<G, 1>(c, P.st.X + (size_t)c_local * ld, x0);
+  if (L.pt == 0) {
+    store_row<G, R>(c, P.st.X + (size_t)c_local * ld, x0);
     if (c.g == 0) { P.st.last_prior[c_local] = last_prior; P.st.last_like[c_local] = last_like; }
   }
 }
 
-template <int G>
-int launch_mtp(const StepParams &P, size_t smem, cudaStream_t stream) {
-  const int threads = 128, chains_per_cta = threads / 32;
+template <int G, int R>
+int launch_mtp(const StepParams &P, cudaStream_t stream) {
+  const int threads = 128, k = P.cfg.multitry;
+  const int chains_per_cta = (threads / 32) * (32 / (k * G));
   const int grid = (P.cfg.nchains_local + chains_per_cta - 1) / chains_per_cta;
-  const bool two_stage = P.st.draw_ws != nullptr;
-  auto kern = two_stage ? dreamzs_mtchain_kernel<G> : dreamzs_mtp_kernel<G>;
+  const size_t chain_b = (size_t)chains_per_cta * ((size_t)k * P.cfg.ld + 3 * DREAMZS_MAX_MULTITRY) * sizeof(double);
+  const size_t table_b = (size_t)((P.table_doubles + 1) & ~1) * sizeof(double);
+  StepParams Q = P;
+  Q.table_in_smem = (table_b + chain_b <= 200 * 1024) ? 1 : 0;
+  Q.nslots = k;
+  const size_t smem = chain_b + (Q.table_in_smem ? table_b : 0);
+  const bool two_stage = Q.st.draw_ws != nullptr;
+  auto kern = two_stage ? dreamzs_mtchain_kernel<G, R> : dreamzs_mtp_kernel<G, R>;
   if (smem > 48 * 1024) {
     static size_t smem_set[2][64] = {{0}};
     if (ensure_dynamic_smem(kern, smem, smem_set[two_stage ? 1 : 0]) != DREAMZS_OK) return DREAMZS_E_LAUNCH;
   }
   if (two_stage) {
-    const int64_t ncts = (int64_t)P.cfg.nchains_local * P.niter, units = ncts * (2 * P.cfg.multitry - 1);
-    dreamzs_mtdraw_scalars_kernel<<<(unsigned)((ncts + 63) / 64), 256, 0, stream>>>(P);
-    dreamzs_mtdraw_kernel<G><<<(unsigned)((units + 256 / G - 1) / (256 / G)), 256, 0, stream>>>(P);
+    constexpr int GD = G * R;          // the draw kernel's lanes per point: one chunk per lane
+    const int64_t ncts = (int64_t)Q.cfg.nchains_local * Q.niter, units = ncts * (2 * k - 1);
+    dreamzs_mtdraw_scalars_kernel<<<(unsigned)((ncts + 63) / 64), 256, 0, stream>>>(Q);
+    dreamzs_mtdraw_kernel<GD><<<(unsigned)((units + 256 / GD - 1) / (256 / GD)), 256, 0, stream>>>(Q);
     if (cudaGetLastError() != cudaSuccess) return DREAMZS_E_LAUNCH;
   }
-  kern<<<grid, threads, smem, stream>>>(P);
+  kern<<<grid, threads, smem, stream>>>(Q);
   return cudaGetLastError() == cudaSuccess ? DREAMZS_OK : DREAMZS_E_LAUNCH;
 }
 

@@ -56,4 +56,19 @@ struct StepParams {
   const double *temperature;   // [nchains_local] per-chain temperature T of astep(q0, T, ...) (Dream.py:193); NULL = 1
 };
 
+// point-parallel multi-try kernels (dreamzs_mtp_kernel.cuh), host side: the layout of a configuration -- lanes per point G, chunk rounds R (G R >= ld / 4, R <= 2), as many chains per
+// warp as fit
+inline bool mtp_layout(int ld, int k, int &G, int &R) {
+  const int chunks = ld / 4;
+  int best = 0;
+  for (int g = 2; g <= 8; g <<= 1)
+    for (int r = 1; r <= 2; ++r) {
+      if (g * r < chunks || k * g > 32) continue;
+      const int cpw = 32 / (k * g);
+      const int score = cpw * 4 - r;          // more chains per warp first, then fewer rounds
+      if (score > best) { best = score; G = g; R = r; }
+    }
+  return best > 0;
+}
+
 }  // namespace dreamzs

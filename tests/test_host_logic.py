@@ -300,8 +300,9 @@ def test_draw_ws_bytes_host_function():
     # multi-try: 8 scalars + (2k-1) points x (A[ld] + B[ld]) doubles per (chain, iteration); C3: 1792 B
     assert f(cfg(), 10) == 4096 * 10 * (8 + 9 * 2 * 12) * 8
     assert f(cfg(multitry=8), 3) == 4096 * 3 * (8 + 15 * 2 * 12) * 8
-    assert f(cfg(ndim=40, ld=40, multitry=4), 1) == 0            # a point needs more than 8 lanes
-    assert f(cfg(ndim=20, ld=20, multitry=5), 1) == 0            # five 8-lane points do not fit a warp
+    assert f(cfg(ndim=40, ld=40, multitry=4), 1) == 4096 * (8 + 7 * 2 * 40) * 8     # 8 lanes x 2 chunks per point, 4 points
+    assert f(cfg(ndim=80, ld=80, multitry=3), 1) == 0            # a point needs more than 8 lanes x 2 chunks
+    assert f(cfg(ndim=40, ld=40, multitry=5), 1) == 0            # five 8-lane points do not fit a warp
     assert f(cfg(flags=_cabi.FLAG_GENERIC_KERNEL), 10) == 0
     # single try: 4 + 2 ld doubles per (chain, iteration), whole windows while they fit the budget
     per = 8192 * (4 + 2 * 200) * 8

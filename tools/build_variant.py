@@ -37,9 +37,9 @@ def main():
     if any(x.startswith('-DDZ_MTP') for x in defs):     # variants of the point-parallel multi-try kernel
         objs = [os.path.join(B.OBJ, f) for f in sorted(os.listdir(B.OBJ)) if f.endswith('.o') and not f.startswith('mtp_')]
         mine = []
-        for g in B.MTP_VARIANTS:
-            o = os.path.join(out, '%s_mtp_%d.o' % (name, g))
-            cmd = [B._nvcc()] + B.NVCC_FLAGS + ['-DDZ_G=%d' % g] + defs + ['-c', os.path.join(B.CSRC, 'dreamzs_mtp_inst.cu'), '-o', o]
+        for g, r in B.MTP_VARIANTS:
+            o = os.path.join(out, '%s_mtp_%d_%d.o' % (name, g, r))
+            cmd = [B._nvcc()] + B.NVCC_FLAGS + ['-DDZ_G=%d' % g, '-DDZ_R=%d' % r] + defs + ['-c', os.path.join(B.CSRC, 'dreamzs_mtp_inst.cu'), '-o', o]
             p = subprocess.run(cmd, capture_output=True, text=True)
             if p.returncode != 0:
                 raise SystemExit(p.stdout + p.stderr)
