@@ -54,7 +54,7 @@ WORKLOADS = {
                kernel='dreamzs_wwin_kernel<32>'),
     'c3': dict(label='C3: 10-D bimodal Gaussian mixture, 4096 chains per GPU, multi-try 5 + snooker', d=10, chains=4096,
                scaling='weak', target='mixture', nseed=2 ** 21, iters_per_step=100, opts=dict(COMMON, multitry=5),
-               seed_dist='normal', kernel='dreamzs_mtchain_kernel<4> (after dreamzs_mtdraw_scalars_kernel + dreamzs_mtdraw_kernel<4>, three launches per window)'),
+               seed_dist='normal', kernel='dreamzs_mtchain_kernel<2,2> (after dreamzs_mtdraw_scalars_kernel + dreamzs_mtdraw_kernel<4>, three launches per window)'),
     'c4': dict(label='C4: 200-D twisted Gaussian (banana, b=0.1), 8192 chains in total', d=200, chains=8192,
                scaling='strong', target='banana', nseed=131072, iters_per_step=100, opts=dict(COMMON, multitry=1),
                seed_dist='banana', kernel='dreamzs_stdraw_kernel<32,2> + dreamzs_stchain_kernel<32,2> (two launches per window)'),
