@@ -1089,7 +1089,7 @@ int launch_wwin_t(StepParams &P, const WwinPlan &pl, int sms, cudaStream_t strea
   }
   const int cap = sms * per_sm;
   int grid = ngroups < cap ? ngroups : cap;
-  if (P.npeers > 0 && P.my_pub && cap >= 2) {   // one more CTA (or the last one) confirms this rank's blocks to the peers
+  if (P.npeers > 0 && cap >= 2) {   // one more CTA (or the last one) confirms this rank's blocks to the peers
     grid = ngroups + 1 < cap ? ngroups + 1 : cap;
     P.ww_confirm = 1;
   }
