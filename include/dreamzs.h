@@ -134,11 +134,13 @@ typedef struct dreamzs_state {
    * chains that shares a CTA).  Without it every window is its own launch. */
   uint32_t *sync_ws;
   int64_t sync_ws_words;
-  /* Optional (may be NULL): scratch of the two-stage multi-try step (multitry > 1, ld <= 32, multitry <= 8 / (ld > 16 ? 2 : 1)):
-   * dreamzs_draw_ws_bytes(cfg, iterations per launch) bytes, 16-byte aligned.  With it a launch is two kernels: one makes
-   * every draw of the window (decisions, archive gathers, e, zeta, crossover masks) for all (chain, iteration, point)
-   * in parallel and leaves them here, the other walks the chains (proposal assembly, log-density, selection,
-   * acceptance).  Without it the fused multi-try kernel does both per chain. */
+  /* Optional (may be NULL): scratch of the two-stage steps, dreamzs_draw_ws_bytes(cfg, iterations per launch) bytes, 16-byte
+   * aligned.  With it a window is two (single try) or three (multi-try) kernels: the draw kernel(s) make every draw of
+   * the window (decisions, archive gathers, e, zeta, crossover masks, the Metropolis / selection uniforms) for all
+   * (chain, iteration[, point]) in parallel and leave them here, the chain kernel walks the chains (proposal assembly,
+   * bounds, log-density, selection, acceptance).  Applies to multitry = 1 with any analytic target (a window is cut into
+   * sub-spans when the scratch holds fewer iterations) and to multitry = k > 1 when a point fits 8 lanes x 2 chunks
+   * (ld <= 64) and k points fit a warp; the dense-Gaussian window kernels do not use it.  Without it the fused kernels run. */
   double *draw_ws;
   int64_t draw_ws_bytes;
 } dreamzs_state;
